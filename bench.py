@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 VQ bottleneck (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --sweep                                   # config-3 microbench table -> stderr/file
+
+A "step" is one pass of the hot path over one batch of synthetic input: the quantiser's training step
+(nearest-code search + gather + commitment loss + EMA statistics/update [+ packed all-reduce when
+N > 1] + straight-through/commitment backward) on the quantiser input of BASELINE config 2
+(VQ-W-Net training step, batch 16 of 256x256 slices -> z = 16x64x256x256, K = 512): 1,048,576
+lookups per GPU per step (weak scaling: 16 slices per GPU).
+
+One JSON line on stdout (rank 0).  `value` = whole-job lookups/s with inputs resident in HBM;
+`e2e` = the same through the module's public API with HOST (pinned) input and the result (loss +
+code map) read back every step; `roofline` = the dominant kernel (nearest-code search) against the
+measured HBM peak; `cpu_baseline` = the oracle (a port of the reference's torch op chain) on the
+host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# BASELINE config 2 quantiser shape
+CFG = dict(B=16, D=64, H=256, K=512, momentum=0.99, eps=1e-5)
+WORKLOADS = {
+    "config2": dict(B=16, D=64, H=256, K=512),
+    "k512d256": dict(B=16, D=256, H=256, K=512),
+    "k64d64": dict(B=16, D=64, H=256, K=64),
+    "k4096d64": dict(B=16, D=64, H=256, K=4096),
+    "k64d256": dict(B=16, D=256, H=256, K=64),
+    "k4096d256": dict(B=16, D=256, H=256, K=4096),
+}
+METRIC = "vq_lookups_per_s"
+UNIT = "lookups/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference op chain on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_factory(wl, slices):
+    from oracle.vq_oracle import OracleVQ
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)
+    D, H, K = wl["D"], wl["H"], wl["K"]
+    m = OracleVQ(D, K, CFG["momentum"], CFG["eps"], "torch", chunk=65536)
+    m.train(True)
+    zs = [torch.randn(slices, D, H, H, generator=g) for _ in range(2)]
+    g_q = torch.randn(slices, D, H, H, generator=g)
+    one = torch.ones(())
+    state = {"i": 0}
+
+    def step():
+        z = zs[state["i"] % 2].requires_grad_(True)
+        state["i"] += 1
+        q, loss, ids = m(z)
+        torch.autograd.grad((q, loss), z, (g_q, one))
+        return loss
+
+    return step, slices * H * H
+
+
+def run_cpu_baseline(wl, budget_s=12.0, slices=1):
+    step, n = cpu_step_factory(wl, slices)
+    step()
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_all < budget_s and len(times) < 50):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{slices} slice(s) of the workload ({n} lookups) per step, quantiser train step "
+                      f"(fwd+EMA+bwd) on CPU, median of {len(times)} steps, {med * 1e3:.1f} ms/step"}
+
+
+def run_reference_arm(args, wl, wl_name):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    slices = 2
+    step, n = cpu_step_factory(wl, slices)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, wl_name, args.gpus, extra={"reference_sample_slices_per_step": slices}),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{slices} slices ({n} lookups) per step; oracle port of vq_module.py on host cores "
+                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(wl, wl_name, gpus, extra=None):
+    c = {"workload": f"{wl_name}: VQ-W-Net quantiser train step (search+gather+loss+EMA+backward), "
+                     f"z = {wl['B']}x{wl['D']}x{wl['H']}x{wl['H']} fp32 per GPU, K = {wl['K']} codes",
+         "slices_per_gpu": wl["B"], "emb_dim": wl["D"], "dict_size": wl["K"], "resolution": wl["H"],
+         "lookups_per_gpu_per_step": wl["B"] * wl["H"] * wl["H"], "parallelism": f"dp{gpus}",
+         "l2": "inputs rotate over 4 buffers of >=268 MB each (> 126 MB L2)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args, wl, wl_name):
+    import torch.distributed as dist
+    import medical_image_editing_b200 as pkg
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the quantiser has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = pkg.lib()
+
+    B, D, H, K = wl["B"], wl["D"], wl["H"], wl["K"]
+    n_per_gpu = B * H * H
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    NBUF = 4
+    zbufs = [torch.randn(B, D, H, H, device=dev, generator=gen).requires_grad_(True) for _ in range(NBUF)]
+    g_q = torch.randn(B, D, H, H, device=dev, generator=gen)
+    one = torch.ones((), device=dev)
+    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch").to(dev)
+    if args.simt:
+        vq.kernel_flags = 1
+    vq.train(True)
+    if world > 1:      # identical codebooks on every rank (DDP would broadcast rank 0's buffers once)
+        for b in vq.buffers():
+            dist.broadcast(b, 0)
+    path = L.vq_assign_path(B, D, H, H, K, vq.kernel_flags)
+
+    def step(i):
+        z = zbufs[i % NBUF]
+        q, loss, ids = vq(z)
+        (g_z,) = torch.autograd.grad((q, loss), z, (g_q, one))
+        return loss, ids, g_z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.vq_profile_enable(1)
+    L.vq_profile_read(None, None)
+    launches0 = L.vq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = L.vq_launch_count() - launches0
+    tot_ms, nl = ctypes.c_double(0), ctypes.c_int(0)
+    L.vq_profile_read(ctypes.byref(tot_ms), ctypes.byref(nl))
+    L.vq_profile_enable(0)
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+
+    # ---- e2e: host (pinned) input -> module -> loss + code map back on the host, every step --------------
+    z_host = torch.randn(B, D, H, H).pin_memory()
+    z_dev = torch.empty(B, D, H, H, device=dev).requires_grad_(True)
+    ids_host = torch.empty(B, H, H, dtype=torch.int64).pin_memory()
+    loss_host = torch.empty(()).pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            z_dev.copy_(z_host, non_blocking=True)
+        q, loss, ids = vq(z_dev)
+        torch.autograd.grad((q, loss), z_dev, (g_q, one))
+        ids_host.copy_(ids, non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result of every step
+
+    e2e_steps = max(1, min(args.steps, 20))
+    e2e_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    s1.record()
+    barrier()
+    t_wall2 = time.time()
+    e2e_ms = s0.elapsed_time(s1)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall2) if sampler else None
+
+    # ---- eval-forward only (the reference's inference path) for the report -------------------
+    vq.eval()
+    with torch.no_grad():
+        for i in range(2):
+            vq(zbufs[i % NBUF])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        fsteps = max(3, min(args.steps, 20))
+        for i in range(fsteps):
+            vq(zbufs[i % NBUF])
+        f1.record()
+        barrier()
+        eval_ms = f0.elapsed_time(f1) / fsteps
+    vq.train(True)
+
+    if rank == 0:
+        hbm, bf16, which = measured_peaks()
+        total_lookups = world * n_per_gpu * args.steps
+        value = total_lookups / (elapsed_ms * 1e-3)
+        alg_bytes = n_per_gpu * (8 * D + 8)                       # read z + write q + int64 id
+        alg_flops = 2.0 * K * D * n_per_gpu
+        avg_kernel_ms = (tot_ms.value / nl.value) if nl.value else None
+        roof = None
+        if avg_kernel_ms:
+            t_hbm = alg_bytes / (hbm * 1e9)
+            t_tc = alg_flops / (bf16 * 1e12)
+            if t_hbm >= t_tc:
+                ach = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+            else:
+                ach = alg_flops / (avg_kernel_ms * 1e-3) / 1e12
+                roof = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16}
+            roof.update({"traffic": None, "kernel": "vq_assign_tc" if path == 1 else "vq_assign_simt",
+                         "kernel_ms": avg_kernel_ms, "launches_timed": nl.value,
+                         "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
+                         "peak_source": f"MEASURED_PEAKS.json ({which})"})
+        cpu = run_cpu_baseline(wl) if (world == 1 and not args.no_cpu) else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl, wl_name, world, extra={"search_path": "tcgen05+fp32-rerank" if path == 1 else "fp32-cuda-core"}),
+            "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core search")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl, args.workload)
+    else:
+        run_b200_arm(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

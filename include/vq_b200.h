@@ -1,0 +1,138 @@
+/*
+ * vq_b200.h -- C-ABI of the B200-native vector-quantisation bottleneck.
+ *
+ * Drop-in boundary for the quantiser of Kaz-K/medical-image-editing
+ * (reference: src/networks/vq/vq_module.py, src/networks/vq/grad_approximation.py).
+ * The reference has no FFI of its own (it is pure PyTorch); these entry points are what a
+ * ctypes binding inside `src/functions/vq_function.py` binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says HOST;
+ *   - the caller owns all memory, including the workspace (size from vq_workspace_bytes);
+ *   - the library never allocates device memory, never synchronises, never touches the
+ *     default stream: every call only enqueues kernels on `stream`;
+ *   - return value 0 = success, negative = error; the message is in vq_last_error()
+ *     (thread-local).  No C++ exception crosses the boundary;
+ *   - fp32 everywhere (reference runs without AMP, run_vqwnet.py:112);
+ *   - there is no CPU fallback.
+ */
+#ifndef VQ_B200_H_
+#define VQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without pulling in the CUDA headers. */
+typedef void* vq_stream_t;
+
+/* error codes */
+#define VQ_OK                 0
+#define VQ_ERR_INVALID_ARG   -1
+#define VQ_ERR_WORKSPACE     -2
+#define VQ_ERR_CUDA          -3
+#define VQ_ERR_UNSUPPORTED   -4
+
+/* vq_assign_fwd flags */
+#define VQ_FLAG_FORCE_SIMT    1   /* use the exact fp32 CUDA-core search (no tensor cores)   */
+#define VQ_FLAG_FORCE_TC      2   /* fail instead of silently choosing the CUDA-core search */
+
+/* vq_lookup layouts */
+#define VQ_LAYOUT_ROWS        0   /* out[n, D]  (F.embedding layout, vq_module.py:203-206)  */
+#define VQ_LAYOUT_NCHW_T      1   /* ids [B,A,C] -> out [B,D,C,A]  contiguous: the tensor the
+                                     callers build with lookup(ids).transpose(1,-1)
+                                     (unet_encoder.py:120-123, vqwnet.py:158)               */
+
+/* Library / ABI version (major*1000 + minor). */
+int vq_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* vq_last_error(void);
+
+/* Which search kernel vq_assign_fwd would use for this shape: 0 = fp32 CUDA-core,
+ * 1 = tcgen05 tensor-core + exact fp32 re-rank. */
+int vq_assign_path(int B, int D, int H, int W, int K, int flags);
+
+/* Workspace bytes needed by vq_assign_fwd for N = B*H*W vectors. */
+size_t vq_workspace_bytes(int64_t N, int K, int D);
+
+/* Floats in the packed statistics buffer: [cnt_hi K | cnt_lo K | sums K*D]
+ * (count = cnt_hi*4096 + cnt_lo, both halves stay exactly representable in fp32 under an
+ * all-reduce(sum) over <= 4096 ranks). */
+size_t vq_stats_floats(int K, int D);
+
+/*
+ * Nearest-code assignment, gather, commitment loss and (optionally) EMA statistics in one
+ * pass over z.  Replaces VQModule._quantize + F.mse_loss (vq_module.py:159-186):
+ *   flatten / k_nearest_neighbor(l2,k=1) / one_hot / lookup / one_hot.sum / flatten.T@one_hot.
+ *
+ *   z        [B,D,H,W] contiguous NCHW
+ *   embed    [K,D]     the codebook (read-only here; q is gathered from THIS codebook,
+ *                      i.e. pre-EMA-update, as vq_module.py:179 precedes :199)
+ *   ids      [B,W,H]   int64, the reference's layout: ids[b,i,j] = code of pixel (h=j,w=i)
+ *                      (vq_module.py:171,178 -- callers do transpose(ids,1,2))
+ *   ids_nat  [B,H,W]   int32, natural order (kept for the backward pass); may be NULL
+ *   q        [B,D,H,W] contiguous NCHW quantised output; may be NULL
+ *   loss     scalar    mean((z-q)^2) over B*D*H*W  (F.mse_loss, vq_module.py:163); may be NULL
+ *   stats    packed [cnt_hi K | cnt_lo K | sums K*D] (see vq_stats_floats), sums[k*D+d] =
+ *            sum of z over pixels assigned to k (== embed_sum[d,k], vq_module.py:185);
+ *            NULL in eval mode
+ *   embed_snapshot [K,D] copy of the codebook used for this call (backward needs the
+ *            pre-update codebook); may be NULL
+ */
+int vq_assign_fwd(const float* z, int B, int D, int H, int W,
+                  const float* embed, int K,
+                  int64_t* ids, int32_t* ids_nat, float* q, float* loss,
+                  float* stats, float* embed_snapshot,
+                  void* workspace, size_t workspace_bytes, int flags, vq_stream_t stream);
+
+/*
+ * EMA codebook update from (possibly all-reduced) packed statistics.  Replaces
+ * vq_module.py:194-199 (exponential_moving_average_ x2, Laplace smoothing, embed refresh).
+ *   cluster_size [K], embed_avg [D,K], embed [K,D]: the module's three buffers, updated in place
+ *   count_scale / sum_scale: multiply counts / sums before the update (1 for a single rank
+ *   or global-batch semantics, 1/world_size for the reference's mean semantics)
+ *   scratch: >= 16 bytes of device memory
+ */
+int vq_ema_update(float* cluster_size, float* embed_avg, float* embed,
+                  const float* stats, int K, int D, float momentum, float eps,
+                  float count_scale, float sum_scale, void* scratch, vq_stream_t stream);
+
+/*
+ * Backward of the whole module: straight-through estimator + commitment loss
+ * (grad_approximation.py:7-29, F.mse_loss backward):
+ *   g_z = g_q + g_loss * 2 * (z - embed_snapshot[ids]) / (B*D*H*W)
+ *   g_q may be NULL (treated as 0); g_loss is a device scalar, may be NULL (treated as 0).
+ */
+int vq_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat,
+           const float* embed_snapshot, float* g_z,
+           int B, int D, int H, int W, int K, vq_stream_t stream);
+
+/*
+ * Codebook gather.  Replaces VQModule.lookup = F.embedding(ids, embed) (vq_module.py:203-206).
+ *   ids int64, n elements (for VQ_LAYOUT_NCHW_T: n = B*A*C with dims given by B,A,C);
+ *   returns VQ_ERR_INVALID_ARG if K<=0; ids are range-checked on the device and an
+ *   out-of-range id sets *status (device int, may be NULL) to 1 and writes zeros.
+ */
+int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D,
+              float* out, int layout, int B, int A, int C, int* status, vq_stream_t stream);
+
+/*
+ * Measurement hooks (used by bench.py only; they do not change results).
+ *   vq_launch_count     number of kernels this library has launched in this process so far.
+ *   vq_profile_enable   when on, vq_assign_fwd brackets its dominant kernel (the nearest-code
+ *                       search) with CUDA events recorded on the caller's stream.
+ *   vq_profile_read     HOST outputs: total milliseconds and number of bracketed launches since
+ *                       the last read; synchronises on the recorded events, then resets.
+ */
+int64_t vq_launch_count(void);
+int vq_profile_enable(int on);
+int vq_profile_read(double* total_ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_B200_H_ */

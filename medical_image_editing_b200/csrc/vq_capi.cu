@@ -1,0 +1,110 @@
+// vq_capi.cu -- the C-ABI (include/vq_b200.h).  Argument checking + kernel sequencing only.
+#include <string.h>
+
+#include "vq_common.cuh"
+
+using namespace vqb200;
+
+extern "C" {
+
+int vq_version(void) { return 1000; }
+
+const char* vq_last_error(void) { return get_error(); }
+
+size_t vq_stats_floats(int K, int D) { return (size_t)2 * (size_t)K + (size_t)K * (size_t)D; }
+
+size_t vq_workspace_bytes(int64_t N, int K, int D) {
+  if (N < 0 || K <= 0 || D <= 0) return 0;
+  return carve_workspace(nullptr, N, K, D).bytes;
+}
+
+int vq_assign_path(int B, int D, int H, int W, int K, int flags) {
+  if (flags & VQ_FLAG_FORCE_SIMT) return 0;
+  return tc_path_supported(B, D, H, W, K) ? 1 : 0;
+}
+
+int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed, int K, int64_t* ids,
+                  int32_t* ids_nat, float* q, float* loss, float* stats, float* embed_snapshot, void* workspace,
+                  size_t workspace_bytes, int flags, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B >= 0 && D > 0 && H >= 0 && W >= 0 && K > 0, VQ_ERR_INVALID_ARG,
+             "vq_assign_fwd: bad shape B=%d D=%d H=%d W=%d K=%d", B, D, H, W, K);
+  VQ_REQUIRE(embed != nullptr && workspace != nullptr, VQ_ERR_INVALID_ARG, "vq_assign_fwd: null embed/workspace");
+  VQ_REQUIRE(((uintptr_t)workspace & 255) == 0, VQ_ERR_INVALID_ARG, "vq_assign_fwd: workspace must be 256-byte aligned");
+  const int64_t N = (int64_t)B * H * W;
+  VQ_REQUIRE(N < (int64_t)1 << 31, VQ_ERR_UNSUPPORTED, "vq_assign_fwd: B*H*W must be < 2^31");
+  VQ_REQUIRE((int64_t)D * H * W < (int64_t)1 << 31, VQ_ERR_UNSUPPORTED, "vq_assign_fwd: D*H*W must be < 2^31");
+  const size_t need = vq_workspace_bytes(N, K, D);
+  VQ_REQUIRE(workspace_bytes >= need, VQ_ERR_WORKSPACE, "vq_assign_fwd: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+  VQ_REQUIRE(N == 0 || z != nullptr, VQ_ERR_INVALID_ARG, "vq_assign_fwd: null z");
+  if (stats) VQ_REQUIRE(((uintptr_t)stats & 15) == 0, VQ_ERR_INVALID_ARG, "vq_assign_fwd: stats must be 16-byte aligned");
+
+  FwdArgs a;
+  a.z = z; a.B = B; a.D = D; a.H = H; a.W = W; a.embed = embed; a.K = K;
+  a.ids = ids; a.ids_nat = ids_nat; a.q = q; a.loss = loss; a.stats = stats; a.snapshot = embed_snapshot;
+  a.ws = carve_workspace(workspace, N, K, D);
+  cudaStream_t s = (cudaStream_t)stream;
+
+  bool use_tc = !(flags & VQ_FLAG_FORCE_SIMT) && tc_path_supported(B, D, H, W, K);
+  if ((flags & VQ_FLAG_FORCE_TC) && !use_tc) {
+    set_error("vq_assign_fwd: tensor-core path unsupported for B=%d D=%d H=%d W=%d K=%d", B, D, H, W, K);
+    return VQ_ERR_UNSUPPORTED;
+  }
+  int rc = launch_prep(a, use_tc, s);
+  if (rc) return rc;
+  if (N > 0) {
+    if (use_tc) {
+      rc = launch_assign_tc(a, s);           // tcgen05 approximate search + exact fp32 re-rank
+      if (rc) return rc;
+      rc = launch_assign_simt(a, /*fallback_list_mode=*/true, s);   // rows the bound could not decide
+      if (rc) return rc;
+    } else {
+      rc = launch_assign_simt(a, false, s);
+      if (rc) return rc;
+    }
+  }
+  return launch_finish(a, s);
+}
+
+int vq_ema_update(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                  float momentum, float eps, float count_scale, float sum_scale, void* scratch, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(K > 0 && D > 0, VQ_ERR_INVALID_ARG, "vq_ema_update: bad shape K=%d D=%d", K, D);
+  VQ_REQUIRE(cluster_size && embed_avg && embed && stats && scratch, VQ_ERR_INVALID_ARG, "vq_ema_update: null pointer");
+  return launch_ema(cluster_size, embed_avg, embed, stats, K, D, momentum, eps, count_scale, sum_scale,
+                    (float*)scratch, (cudaStream_t)stream);
+}
+
+int vq_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat, const float* embed_snapshot,
+           float* g_z, int B, int D, int H, int W, int K, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B >= 0 && D > 0 && H >= 0 && W >= 0 && K > 0, VQ_ERR_INVALID_ARG, "vq_bwd: bad shape");
+  if ((int64_t)B * H * W == 0) return VQ_OK;
+  VQ_REQUIRE(z && ids_nat && embed_snapshot && g_z, VQ_ERR_INVALID_ARG, "vq_bwd: null pointer");
+  return launch_bwd(g_q, g_loss, z, ids_nat, embed_snapshot, g_z, B, D, H, W, K, (cudaStream_t)stream);
+}
+
+int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout, int B, int A,
+              int C, int* status, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(K > 0 && D > 0 && n >= 0, VQ_ERR_INVALID_ARG, "vq_lookup: bad shape n=%lld K=%d D=%d", (long long)n, K, D);
+  VQ_REQUIRE(layout == VQ_LAYOUT_ROWS || layout == VQ_LAYOUT_NCHW_T, VQ_ERR_INVALID_ARG, "vq_lookup: bad layout %d", layout);
+  if (n == 0) return VQ_OK;
+  VQ_REQUIRE(ids && embed && out, VQ_ERR_INVALID_ARG, "vq_lookup: null pointer");
+  if (layout == VQ_LAYOUT_NCHW_T)
+    VQ_REQUIRE((int64_t)B * A * C == n && B <= 65535 && (C + 31) / 32 <= 65535, VQ_ERR_INVALID_ARG,
+               "vq_lookup: B*A*C != n (or grid too large)");
+  return launch_lookup(ids, n, embed, K, D, out, layout, B, A, C, status, (cudaStream_t)stream);
+}
+
+int64_t vq_launch_count(void) { return (int64_t)launch_count(); }
+
+int vq_profile_enable(int on) {
+  profile_enable(on != 0);
+  return VQ_OK;
+}
+
+int vq_profile_read(double* total_ms, int* launches) { return profile_read(total_ms, launches); }
+
+}  // extern "C"

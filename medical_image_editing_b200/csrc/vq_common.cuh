@@ -1,0 +1,120 @@
+// vq_common.cuh -- shared declarations for the B200 VQ bottleneck kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/vq_b200.h"
+
+namespace vqb200 {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, negative return codes; nothing throws across the C-ABI)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VQ_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::vqb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                          __FILE__, __LINE__);                                           \
+      return VQ_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define VQ_REQUIRE(cond, code, ...)                                                      \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::vqb200::set_error(__VA_ARGS__);                                                  \
+      return (code);                                                                     \
+    }                                                                                    \
+  } while (0)
+
+// measurement hooks (vq_launch_count / vq_profile_*)
+void count_launch(int n = 1);
+long long launch_count();
+void profile_enable(bool on);
+bool profile_begin(cudaStream_t s);   // records the start event if profiling is on
+void profile_end(cudaStream_t s);     // records the stop event
+int profile_read(double* total_ms, int* launches);
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (caller-owned memory, carved here; every region 256-byte aligned)
+// ---------------------------------------------------------------------------------------------
+constexpr int kCodePad = 256;  // codebook padded to a multiple of this many codes
+
+struct Workspace {
+  float* e2;         // [Kpad]   |e_k|^2, +inf for padding codes
+  float* et;         // [D][Kpad] transposed codebook (0 for padding codes) -- SIMT search operand
+  double* loss_acc;  // [1]      sum (z-q)^2
+  int* counts;       // [K]      exact int32 histogram
+  int* misc;         // [8]      misc[0] = number of rows routed to the exact fallback search
+  int* fb_rows;      // [N]      rows routed to the exact fallback search (tensor-core path)
+  float* tc_e;       // tensor-core operand: codebook + augmentation columns, see vq_assign_tc.cu
+  float* tc_meta;    // [16]     per-call scalars for the tensor-core path (bounds)
+  size_t bytes;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int pad_codes(int K) { return (int)align_up((size_t)K, kCodePad); }
+inline int tc_dpad(int D) { return (int)align_up((size_t)D + 8, 32); }   // D + 8 augmentation columns
+
+inline Workspace carve_workspace(void* base, int64_t N, int K, int D) {
+  Workspace w;
+  const int Kpad = pad_codes(K);
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
+  w.e2 = (float*)take(sizeof(float) * Kpad);
+  w.et = (float*)take(sizeof(float) * (size_t)D * Kpad);
+  w.loss_acc = (double*)take(sizeof(double));
+  w.counts = (int*)take(sizeof(int) * K);
+  w.misc = (int*)take(sizeof(int) * 8);
+  w.fb_rows = (int*)take(sizeof(int) * (size_t)(N > 0 ? N : 1));
+  w.tc_e = (float*)take(sizeof(float) * (size_t)Kpad * tc_dpad(D));
+  w.tc_meta = (float*)take(sizeof(float) * 16);
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (each only enqueues on `stream`; returns a VQ_* code)
+// ---------------------------------------------------------------------------------------------
+struct FwdArgs {
+  const float* z; int B, D, H, W;
+  const float* embed; int K;
+  int64_t* ids; int32_t* ids_nat; float* q; float* loss; float* stats; float* snapshot;
+  Workspace ws;
+};
+
+int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s);
+int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s);
+int launch_assign_tc(const FwdArgs& a, cudaStream_t s);          // vq_assign_tc.cu
+bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc.cu
+int launch_finish(const FwdArgs& a, cudaStream_t s);
+int launch_ema(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+               float momentum, float eps, float count_scale, float sum_scale, float* scratch, cudaStream_t s);
+int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat,
+               const float* snap, float* g_z, int B, int D, int H, int W, int K, cudaStream_t s);
+int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout,
+                  int B, int A, int C, int* status, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The reference's score for code k and query z (vq_module.py:54-57):
+//   s = fl( fl(2*dot) - |e|^2 ) - |z|^2     (2*dot is exact in binary fp)
+__device__ __forceinline__ float ref_score(float dot, float e2, float z2) {
+  return __fsub_rn(__fmaf_rn(2.0f, dot, -e2), z2);
+}
+
+}  // namespace vqb200

@@ -1,0 +1,638 @@
+// vq_kernels.cu -- fp32 CUDA-core kernels of the VQ bottleneck (sm_100a):
+//   prep        |e|^2, transposed codebook, snapshot, accumulator zeroing
+//   assign_simt exact fp32 nearest-code search (+ gather, loss, EMA statistics) -- the first
+//               correct path and the exact fallback of the tensor-core path
+//   finish      loss finalisation + packing of the int32 histogram
+//   ema         EMA / Laplace-smoothing / codebook refresh            (vq_module.py:194-199)
+//   bwd         straight-through + commitment-loss backward          (grad_approximation.py:7-29)
+//   lookup      codebook gather                                      (vq_module.py:203-206)
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "vq_common.cuh"
+
+namespace vqb200 {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = {0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// measurement hooks
+// ---------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open = nullptr;
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+void profile_enable(bool on) { g_prof_on.store(on); }
+
+static cudaEvent_t prof_get_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+bool profile_begin(cudaStream_t s) {
+  if (!g_prof_on.load()) return false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_events.size() >= 8192) return false;
+  g_prof_open = prof_get_event();
+  if (!g_prof_open) return false;
+  cudaEventRecord(g_prof_open, s);
+  return true;
+}
+void profile_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_open) return;
+  cudaEvent_t e = prof_get_event();
+  if (e) { cudaEventRecord(e, s); g_prof_events.emplace_back(g_prof_open, e); }
+  else g_prof_pool.push_back(g_prof_open);
+  g_prof_open = nullptr;
+}
+int profile_read(double* total_ms, int* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0; int n = 0;
+  for (auto& pr : g_prof_events) {
+    if (cudaEventSynchronize(pr.second) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; ++n; }
+    }
+    g_prof_pool.push_back(pr.first); g_prof_pool.push_back(pr.second);
+  }
+  g_prof_events.clear();
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return VQ_OK;
+}
+
+// =============================================================================================
+// prep
+// =============================================================================================
+__global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kpad,
+                               float* __restrict__ e2, float* __restrict__ et, float* __restrict__ snap,
+                               float* __restrict__ stats, size_t stats_n, int* __restrict__ counts,
+                               double* __restrict__ loss_acc, int* __restrict__ misc) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  // |e_k|^2 : one thread per code, ascending d, fused multiply-add chain
+  for (size_t k = tid; k < (size_t)Kpad; k += nth) {
+    float acc = 0.f;
+    if (k < (size_t)K) {
+      const float* row = E + k * D;
+      for (int d = 0; d < D; ++d) acc = __fmaf_rn(row[d], row[d], acc);
+    } else {
+      acc = INFINITY;  // padding codes can never win: score = 2*0 - inf
+    }
+    e2[k] = acc;
+  }
+  // transposed codebook (coalesced writes) and snapshot
+  const size_t tot = (size_t)D * Kpad;
+  for (size_t i = tid; i < tot; i += nth) {
+    const size_t d = i / Kpad, k = i % Kpad;
+    et[i] = (k < (size_t)K) ? E[k * D + d] : 0.f;
+  }
+  if (snap) {
+    const size_t kd = (size_t)K * D;
+    for (size_t i = tid; i < kd; i += nth) snap[i] = E[i];
+  }
+  if (stats) {
+    for (size_t i = tid; i < stats_n; i += nth) stats[i] = 0.f;
+  }
+  for (size_t i = tid; i < (size_t)K; i += nth) counts[i] = 0;
+  if (tid == 0) *loss_acc = 0.0;
+  if (tid < 8) misc[tid] = 0;
+}
+
+// =============================================================================================
+// exact fp32 search
+// =============================================================================================
+constexpr int SIMT_TP = 128;   // pixels per tile
+constexpr int SIMT_TK = 64;    // codes per pass
+constexpr int SIMT_DC = 32;    // channel chunk
+
+// One CTA (256 threads) = 128 pixels.  Thread (tx = tid&31, ty = tid>>5) owns pixels 4tx..4tx+3
+// and, in each pass over 64 codes, codes 8ty..8ty+7: a 4x8 register tile of dot products,
+// accumulated over ascending d with one fma chain per (pixel, code).
+__global__ void __launch_bounds__(256)
+vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et, const float* __restrict__ e2,
+                      const float* __restrict__ E, int B, int D, int H, int W, int K, int Kpad,
+                      const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
+                      int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat, float* __restrict__ q,
+                      double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums) {
+  __shared__ __align__(16) float zs[SIMT_DC][SIMT_TP];
+  __shared__ __align__(16) float es[SIMT_DC][SIMT_TK];
+  __shared__ float e2s[SIMT_TK];
+  __shared__ float red_s[8][SIMT_TP];
+  __shared__ int red_i[8][SIMT_TP];
+  __shared__ long long pix_off[SIMT_TP];   // offset of z[b,0,p]; -1 = masked
+
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int HW = H * W;
+  const long long N = (long long)B * HW;
+
+  long long ntiles;
+  const bool list_mode = (fb_rows != nullptr);
+  int nrows = 0;
+  if (list_mode) {
+    nrows = *fb_count;
+    ntiles = (nrows + SIMT_TP - 1) / SIMT_TP;
+  } else {
+    ntiles = (long long)B * ((HW + SIMT_TP - 1) / SIMT_TP);
+  }
+  const int tiles_per_img = (HW + SIMT_TP - 1) / SIMT_TP;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    if (tid < SIMT_TP) {
+      long long off = -1;
+      if (list_mode) {
+        const long long r = tile * SIMT_TP + tid;
+        if (r < nrows) {
+          const long long n = fb_rows[r];
+          const long long b = n / HW, p = n % HW;
+          off = b * (long long)D * HW + p;
+        }
+      } else {
+        const long long b = tile / tiles_per_img;
+        const long long p = (tile % tiles_per_img) * SIMT_TP + tid;
+        if (p < HW) off = b * (long long)D * HW + p;
+      }
+      pix_off[tid] = off;
+    }
+    __syncthreads();
+
+    float best[4];
+    int bidx[4];
+    float z2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = -INFINITY; bidx[i] = 0; }
+
+    // loader mapping: pixel i = tid & 127, rows dd = (tid >> 7) + 2*j
+    const int li = tid & (SIMT_TP - 1);
+    const long long loff = pix_off[li];
+
+    for (int cb = 0; cb < Kpad; cb += SIMT_TK) {
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+
+      for (int d0 = 0; d0 < D; d0 += SIMT_DC) {
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < SIMT_DC / 2; ++j) {
+          const int dd = (tid >> 7) + 2 * j;
+          const int d = d0 + dd;
+          float v = 0.f;
+          if (d < D && loff >= 0) v = __ldg(z + loff + (long long)d * HW);
+          zs[dd][li] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < (SIMT_DC * SIMT_TK) / 256; ++j) {
+          const int e = tid + j * 256;
+          const int dd = e / SIMT_TK, kk = e % SIMT_TK;
+          const int d = d0 + dd;
+          es[dd][kk] = (d < D) ? __ldg(et + (size_t)d * Kpad + cb + kk) : 0.f;
+        }
+        if (d0 == 0 && tid < SIMT_TK) e2s[tid] = e2[cb + tid];
+        __syncthreads();
+
+        const int dlim = min(SIMT_DC, D - d0);
+        if (cb == 0) {
+          for (int dd = 0; dd < dlim; ++dd) {
+            const float4 zv = *reinterpret_cast<const float4*>(&zs[dd][tx * 4]);
+            z2[0] = __fmaf_rn(zv.x, zv.x, z2[0]);
+            z2[1] = __fmaf_rn(zv.y, zv.y, z2[1]);
+            z2[2] = __fmaf_rn(zv.z, zv.z, z2[2]);
+            z2[3] = __fmaf_rn(zv.w, zv.w, z2[3]);
+          }
+        }
+#pragma unroll 4
+        for (int dd = 0; dd < dlim; ++dd) {
+          const float4 zv = *reinterpret_cast<const float4*>(&zs[dd][tx * 4]);
+          const float4 ea = *reinterpret_cast<const float4*>(&es[dd][ty * 8]);
+          const float4 eb = *reinterpret_cast<const float4*>(&es[dd][ty * 8 + 4]);
+          const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+          const float ee[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(zz[i], ee[c], acc[i][c]);
+        }
+      }
+      // scores for this block of codes, reference op order; strict '>' keeps the lowest index
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = cb + ty * 8 + c;
+        const float ek = e2s[ty * 8 + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float s = ref_score(acc[i][c], ek, z2[i]);
+          if (s > best[i]) { best[i] = s; bidx[i] = k; }
+        }
+      }
+    }
+
+    // reduce across the 8 code groups of each pixel
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red_s[ty][tx * 4 + i] = best[i];
+      red_i[ty][tx * 4 + i] = bidx[i];
+    }
+    __syncthreads();
+
+    float lsum = 0.f;
+    if (tid < SIMT_TP) {
+      const long long off = pix_off[tid];
+      if (off >= 0) {
+        float bs = red_s[0][tid];
+        int bi = red_i[0][tid];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) {
+          const float s = red_s[g][tid];
+          const int i2 = red_i[g][tid];
+          if (s > bs || (s == bs && i2 < bi)) { bs = s; bi = i2; }
+        }
+        const long long b = off / ((long long)D * HW);
+        const long long p = off - b * (long long)D * HW;
+        const int h = (int)(p / W), w = (int)(p % W);
+        if (ids) ids[b * HW + (long long)w * H + h] = bi;
+        if (ids_nat) ids_nat[b * HW + p] = bi;
+        if (counts) atomicAdd(&counts[bi], 1);
+        const float* erow = E + (size_t)bi * D;
+        float* srow = sums ? sums + (size_t)bi * D : nullptr;
+        if ((D & 3) == 0) {
+          for (int d = 0; d < D; d += 4) {
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(erow + d));
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            float zv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zv[c] = __ldg(z + off + (long long)(d + c) * HW);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float df = zv[c] - ev[c];
+              lsum = __fmaf_rn(df, df, lsum);
+              if (q) q[off + (long long)(d + c) * HW] = ev[c];
+            }
+            if (srow) atomicAdd(reinterpret_cast<float4*>(srow + d), make_float4(zv[0], zv[1], zv[2], zv[3]));
+          }
+        } else {
+          for (int d = 0; d < D; ++d) {
+            const float ev = __ldg(erow + d);
+            const float zv = __ldg(z + off + (long long)d * HW);
+            const float df = zv - ev;
+            lsum = __fmaf_rn(df, df, lsum);
+            if (q) q[off + (long long)d * HW] = ev;
+            if (srow) atomicAdd(srow + d, zv);
+          }
+        }
+      }
+    }
+    if (tid < SIMT_TP) {   // warps 0..3, warp-uniform branch
+      lsum = warp_sum(lsum);
+      if ((tid & 31) == 0 && loss_acc) atomicAdd(loss_acc, (double)lsum);
+    }
+  }
+  (void)N;
+}
+
+// =============================================================================================
+// finish: loss = acc / (N*D); pack the int32 histogram as two exactly-representable floats
+// =============================================================================================
+__global__ void vq_finish_kernel(const double* __restrict__ loss_acc, float* __restrict__ loss, double inv_numel,
+                                 const int* __restrict__ counts, float* __restrict__ stats, int K) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0 && loss) *loss = (float)(*loss_acc * inv_numel);
+  if (stats) {
+    for (int k = tid; k < K; k += gridDim.x * blockDim.x) {
+      const int c = counts[k];
+      stats[k] = (float)(c >> 12);
+      stats[K + k] = (float)(c & 4095);
+    }
+  }
+}
+
+// =============================================================================================
+// EMA update (vq_module.py:132-136, 194-199)
+// =============================================================================================
+__global__ void __launch_bounds__(1024)
+vq_ema_cs_kernel(float* __restrict__ cluster_size, const float* __restrict__ stats, int K, float momentum,
+                 float alpha, float count_scale, float* __restrict__ scratch) {
+  __shared__ double red[32];
+  double part = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float cnt = __fmaf_rn(stats[k], 4096.0f, stats[K + k]);
+    cnt = cnt * count_scale;
+    const float cs = __fmaf_rn(alpha, cnt, __fmul_rn(cluster_size[k], momentum));   // base.mul_(m).add_(u, alpha=1-m)
+    cluster_size[k] = cs;
+    part += (double)cs;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) scratch[0] = (float)v;   // n = cluster_size.sum()
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vq_ema_embed_kernel(const float* __restrict__ cluster_size, float* __restrict__ embed_avg, float* __restrict__ embed,
+                    const float* __restrict__ sums, int K, int D, float momentum, float alpha, float sum_scale,
+                    float eps, float k_eps, const float* __restrict__ scratch) {
+  // 32x32 tile transpose: embed_avg is [D][K] (k fastest), sums / embed are [K][D] (d fastest)
+  __shared__ float t_in[32][33];
+  __shared__ float t_out[32][33];
+  const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8
+  const float n = scratch[0];
+  for (int r = ly; r < 32; r += 8) {            // read sums[k0+r][d0+lx]
+    const int k = k0 + r, d = d0 + lx;
+    t_in[r][lx] = (k < K && d < D) ? sums[(size_t)k * D + d] * sum_scale : 0.f;
+  }
+  __syncthreads();
+  for (int r = ly; r < 32; r += 8) {            // d = d0 + r, k = k0 + lx
+    const int d = d0 + r, k = k0 + lx;
+    if (k < K && d < D) {
+      const size_t ia = (size_t)d * K + k;
+      const float avg = __fmaf_rn(alpha, t_in[lx][r], __fmul_rn(embed_avg[ia], momentum));
+      embed_avg[ia] = avg;
+      const float cs = __fdiv_rn(__fmul_rn(n, __fadd_rn(cluster_size[k], eps)), __fadd_rn(n, k_eps));
+      t_out[lx][r] = __fdiv_rn(avg, cs);
+    }
+  }
+  __syncthreads();
+  for (int r = ly; r < 32; r += 8) {            // write embed[k0+r][d0+lx]
+    const int k = k0 + r, d = d0 + lx;
+    if (k < K && d < D) embed[(size_t)k * D + d] = t_out[r][lx];
+  }
+}
+
+// =============================================================================================
+// backward:  g_z = g_q + g_loss * 2 (z - E[id]) / numel
+// =============================================================================================
+// vector path: thread = 4 consecutive pixels x 4 channels per step
+__global__ void __launch_bounds__(256)
+vq_bwd_vec_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss, const float* __restrict__ z,
+                  const int32_t* __restrict__ ids_nat, const float* __restrict__ E, float* __restrict__ g_z,
+                  int D, int HW, long long nquads, int dsplit, float two_over_numel) {
+  const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (quad >= nquads) return;
+  const int qpi = HW >> 2;
+  const long long b = quad / qpi;
+  const int p = (int)(quad % qpi) << 2;
+  const float coef = g_loss ? (*g_loss) * two_over_numel : 0.f;
+  const int4 id4 = *reinterpret_cast<const int4*>(ids_nat + b * HW + p);
+  const float* e0 = E + (size_t)id4.x * D;
+  const float* e1 = E + (size_t)id4.y * D;
+  const float* e2 = E + (size_t)id4.z * D;
+  const float* e3 = E + (size_t)id4.w * D;
+  const int dper = D / dsplit;                 // multiple of 4 by construction
+  const int dbeg = blockIdx.y * dper, dend = dbeg + dper;
+  const long long base = b * (long long)D * HW + p;
+  for (int d = dbeg; d < dend; d += 4) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(e0 + d));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(e1 + d));
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(e2 + d));
+    const float4 a3 = __ldg(reinterpret_cast<const float4*>(e3 + d));
+    const float ev[4][4] = {{a0.x, a1.x, a2.x, a3.x}, {a0.y, a1.y, a2.y, a3.y},
+                            {a0.z, a1.z, a2.z, a3.z}, {a0.w, a1.w, a2.w, a3.w}};
+    float4 zv[4], gv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long o = base + (long long)(d + c) * HW;
+      zv[c] = __ldcs(reinterpret_cast<const float4*>(z + o));
+      gv[c] = g_q ? __ldcs(reinterpret_cast<const float4*>(g_q + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 r;
+      r.x = __fmaf_rn(coef, zv[c].x - ev[c][0], gv[c].x);
+      r.y = __fmaf_rn(coef, zv[c].y - ev[c][1], gv[c].y);
+      r.z = __fmaf_rn(coef, zv[c].z - ev[c][2], gv[c].z);
+      r.w = __fmaf_rn(coef, zv[c].w - ev[c][3], gv[c].w);
+      __stcs(reinterpret_cast<float4*>(g_z + base + (long long)(d + c) * HW), r);
+    }
+  }
+}
+
+// generic path: thread = one pixel, all channels
+__global__ void __launch_bounds__(256)
+vq_bwd_generic_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss, const float* __restrict__ z,
+                      const int32_t* __restrict__ ids_nat, const float* __restrict__ E, float* __restrict__ g_z,
+                      int D, int HW, long long N, float two_over_numel) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long b = n / HW;
+  const int p = (int)(n % HW);
+  const float coef = g_loss ? (*g_loss) * two_over_numel : 0.f;
+  const float* e = E + (size_t)ids_nat[n] * D;
+  const long long base = b * (long long)D * HW + p;
+  for (int d = 0; d < D; ++d) {
+    const long long o = base + (long long)d * HW;
+    const float g = g_q ? g_q[o] : 0.f;
+    g_z[o] = __fmaf_rn(coef, z[o] - __ldg(e + d), g);
+  }
+}
+
+// =============================================================================================
+// lookup
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+vq_lookup_rows_kernel(const int64_t* __restrict__ ids, long long n, const float* __restrict__ E, int K, int D,
+                      float* __restrict__ out, int* __restrict__ status) {
+  // thread = (row, 4-channel group) when D%4==0, else (row, channel)
+  const int vec = ((D & 3) == 0) ? 4 : 1;
+  const int gpr = D / vec;
+  const long long total = n * gpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / gpr;
+    const int g = (int)(i % gpr);
+    const long long id = ids[r];
+    const bool ok = (id >= 0 && id < K);
+    if (!ok && status) *status = 1;
+    if (vec == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = __ldg(reinterpret_cast<const float4*>(E + (size_t)id * D) + g);
+      __stcs(reinterpret_cast<float4*>(out + r * D) + g, v);
+    } else {
+      out[r * D + g] = ok ? __ldg(E + (size_t)id * D + g) : 0.f;
+    }
+  }
+}
+
+// ids [B,A,C] -> out [B,D,C,A]: out[b,d,c,a] = E[ids[b,a,c]][d].  Tile: 32 a x 32 c per CTA so that
+// both the id reads (c fastest) and the output writes (a fastest) are coalesced.
+__global__ void __launch_bounds__(256)
+vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, int K, int D,
+                        float* __restrict__ out, int B, int A, int C, int* __restrict__ status) {
+  __shared__ int sid[32][33];
+  const int a0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int r = ly; r < 32; r += 8) {     // a = a0 + r, c = c0 + lx
+    const int a = a0 + r, c = c0 + lx;
+    int v = -1;
+    if (a < A && c < C) {
+      const long long id = ids[((long long)b * A + a) * C + c];
+      if (id >= 0 && id < K) v = (int)id;
+      else if (status) *status = 1;
+    }
+    sid[r][lx] = v;
+  }
+  __syncthreads();
+  // thread: a = a0 + lx (fastest in output), c = c0 + r
+  for (int r = ly; r < 32; r += 8) {
+    const int a = a0 + lx, c = c0 + r;
+    if (a < A && c < C) {
+      const int id = sid[lx][r];
+      const float* e = E + (size_t)(id < 0 ? 0 : id) * D;
+      float* o = out + (((long long)b * D) * C + c) * A + a;
+      const long long dstride = (long long)C * A;
+      for (int d = 0; d < D; ++d) o[d * dstride] = (id < 0) ? 0.f : __ldg(e + d);
+    }
+  }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_prep(const FwdArgs& a, bool /*tc_path*/, cudaStream_t s) {
+  const int Kpad = pad_codes(a.K);
+  const size_t work = (size_t)a.D * Kpad;
+  int blocks = (int)((work + 255) / 256);
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  if (blocks < 1) blocks = 1;
+  const size_t stats_n = a.stats ? vq_stats_floats(a.K, a.D) : 0;
+  vq_prep_kernel<<<blocks, 256, 0, s>>>(a.embed, a.K, a.D, Kpad, a.ws.e2, a.ws.et, a.snapshot, a.stats, stats_n,
+                                        a.ws.counts, a.ws.loss_acc, a.ws.misc);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s) {
+  const int HW = a.H * a.W;
+  const int Kpad = pad_codes(a.K);
+  long long ntiles = (long long)a.B * ((HW + SIMT_TP - 1) / SIMT_TP);
+  int blocks;
+  if (fallback_list_mode) {
+    blocks = 2 * sm_count();          // grid-stride over a device-side row count
+  } else {
+    blocks = (int)(ntiles < (long long)8 * sm_count() ? ntiles : (long long)8 * sm_count());
+  }
+  if (blocks < 1) blocks = 1;
+  float* sums = a.stats ? a.stats + 2 * (size_t)a.K : nullptr;
+  const bool prof = !fallback_list_mode && profile_begin(s);
+  vq_assign_simt_kernel<<<blocks, 256, 0, s>>>(a.z, a.ws.et, a.ws.e2, a.embed, a.B, a.D, a.H, a.W, a.K, Kpad,
+                                               fallback_list_mode ? a.ws.fb_rows : nullptr, a.ws.misc,
+                                               a.ids, a.ids_nat, a.q, a.ws.loss_acc,
+                                               a.stats ? a.ws.counts : nullptr, sums);
+  if (prof) profile_end(s);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_finish(const FwdArgs& a, cudaStream_t s) {
+  const double numel = (double)a.B * a.D * a.H * a.W;
+  const int blocks = a.stats ? (a.K + 255) / 256 : 1;
+  vq_finish_kernel<<<blocks, 256, 0, s>>>(a.ws.loss_acc, a.loss, 1.0 / numel, a.ws.counts, a.stats, a.K);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_ema(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+               float momentum, float eps, float count_scale, float sum_scale, float* scratch, cudaStream_t s) {
+  const float alpha = (float)(1.0 - (double)momentum);
+  const float k_eps = (float)((double)K * (double)eps);
+  vq_ema_cs_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, momentum, alpha, count_scale, scratch);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  dim3 grid((K + 31) / 32, (D + 31) / 32);
+  vq_ema_embed_kernel<<<grid, 256, 0, s>>>(cluster_size, embed_avg, embed, stats + 2 * (size_t)K, K, D, momentum,
+                                           alpha, sum_scale, eps, k_eps, scratch);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat, const float* snap,
+               float* g_z, int B, int D, int H, int W, int K, cudaStream_t s) {
+  (void)K;
+  const int HW = H * W;
+  const long long N = (long long)B * HW;
+  const float two_over_numel = (float)(2.0 / ((double)N * D));
+  auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+  const bool vec = (HW % 4 == 0) && (D % 4 == 0) && al16(z) && al16(g_z) && (!g_q || al16(g_q)) && al16(ids_nat) &&
+                   al16(snap);
+  if (vec) {
+    const long long nquads = N / 4;
+    const long long bx = (nquads + 255) / 256;
+    // split the channel loop across blockIdx.y until the grid has a few waves
+    int dsplit = 1;
+    while (bx * dsplit < 4LL * sm_count() && (D / (dsplit * 2)) % 4 == 0 && D / (dsplit * 2) >= 4) dsplit *= 2;
+    dim3 grid((unsigned)bx, (unsigned)dsplit);
+    vq_bwd_vec_kernel<<<grid, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, nquads, dsplit, two_over_numel);
+  } else {
+    const long long bx = (N + 255) / 256;
+    vq_bwd_generic_kernel<<<(unsigned)bx, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, N, two_over_numel);
+  }
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout, int B,
+                  int A, int C, int* status, cudaStream_t s) {
+  if (n == 0) return VQ_OK;
+  if (layout == VQ_LAYOUT_ROWS) {
+    const bool al = ((((uintptr_t)embed) | ((uintptr_t)out)) & 15) == 0;
+    if ((D & 3) == 0 && !al) {
+      set_error("vq_lookup: embed/out must be 16-byte aligned when D %% 4 == 0");
+      return VQ_ERR_INVALID_ARG;
+    }
+    const long long total = (long long)n * (((D & 3) == 0) ? D / 4 : D);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    vq_lookup_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(ids, n, embed, K, D, out, status);
+  } else {
+    dim3 grid((A + 31) / 32, (C + 31) / 32, B);
+    vq_lookup_nchw_t_kernel<<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+  }
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+}  // namespace vqb200

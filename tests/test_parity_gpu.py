@@ -1,0 +1,383 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the module / autograd Function) against
+ (1) golden vectors produced by the unmodified reference (tests/golden),
+ (2) the CPU oracle on seeded inputs at sizes it finishes in seconds,
+ (3) size-independent properties at BASELINE.json's full sizes.
+Bars (BASELINE.json north_star): ids and counts bit-exact; quantized bit-exact (pure gather);
+loss / gradients / EMA buffers within 1e-5 relative in fp32."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import medical_image_editing_b200 as pkg
+from medical_image_editing_b200 import _native
+from oracle.vq_oracle import OracleVQ, seeded_case, make_oracle, score_gap_is_tie
+from util import SMALL_CASES, load_golden, t, rel_err, set_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+DEV = "cuda:0"
+PATHS = [pytest.param(_native.VQ_FLAG_FORCE_SIMT, id="simt"), pytest.param(0, id="auto")]
+
+
+def new_vq(K, D, momentum=0.99, flags=0, **kw):
+    m = pkg.VQ(emb_dim=D, dict_size=K, momentum=momentum, eps=1e-5, knn_backend="torch", **kw).to(DEV)
+    m.kernel_flags = flags
+    return m
+
+
+def assert_ids_match(ids_gpu, ids_ref, embed, z, allow_ties=True):
+    """Bit-exact ids; a differing row is tolerated only if the oracle's own fp32 scores of the two
+    codes are a numerical tie (the reference's tie-break is unspecified)."""
+    a = ids_gpu.cpu().reshape(-1)
+    b = ids_ref.reshape(-1)
+    bad = (a != b).nonzero().reshape(-1)
+    if bad.numel() == 0:
+        return 0
+    assert allow_ties, f"{bad.numel()} id mismatches"
+    flat = z.detach().cpu().transpose(1, -1).reshape(-1, z.shape[1])
+    tie = score_gap_is_tie(embed.cpu(), flat[bad], a[bad], b[bad])
+    assert bool(tie.all()), f"{int((~tie).sum())} id mismatches that are not fp32 ties (of {bad.numel()} differing rows)"
+    assert bad.numel() <= max(2, a.numel() // 100000), f"too many tie rows: {bad.numel()}"
+    return int(bad.numel())
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) golden vectors from the reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_golden_forward_backward_ema(name, flags):
+    g = load_golden(name)
+    B, D, H, K, training, steps = [int(x) for x in g["meta"]]
+    m = new_vq(K, D, float(g["momentum"][0]), flags)
+    set_state(m, g["embed0"], g["cluster_size0"], g["embed_avg0"])
+    m.train(bool(training))
+    for s in range(steps):
+        sfx = "" if s == 0 else f"_s{s}"
+        if s > 0:   # re-sync state from the reference each step (1-ulp drift may flip later near-ties)
+            p = "" if s == 1 else f"_s{s - 1}"
+            set_state(m, g["embed1" + p], g["cluster_size1" + p], g["embed_avg1" + p])
+        z = t(g["z" + sfx], DEV).requires_grad_(True)
+        q, loss, ids = m(z)
+        assert q.shape == z.shape and ids.shape == (B, H, H) and ids.dtype == torch.int64 and loss.dim() == 0
+        total = (q * t(g["g_q" + sfx], DEV)).sum() + float(g["w" + sfx][0]) * loss
+        (g_z,) = torch.autograd.grad(total, z)
+        assert torch.equal(ids.cpu(), t(g["ids" + sfx])), "ids must be bit-exact"
+        assert torch.equal(q.detach().cpu(), t(g["q" + sfx])), "quantized must be bit-exact"
+        assert abs(loss.item() - float(g["loss" + sfx][0])) <= TOL * abs(float(g["loss" + sfx][0]))
+        assert rel_err(g_z, t(g["g_z" + sfx])) <= TOL
+        assert rel_err(m.embed, t(g["embed1" + sfx])) <= TOL
+        assert rel_err(m.cluster_size, t(g["cluster_size1" + sfx])) <= TOL
+        assert rel_err(m.embed_avg, t(g["embed_avg1" + sfx])) <= TOL
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_golden_config1_quantiser(flags):
+    """BASELINE config 1 quantiser shape: 1x64x256x256, K=512, against the reference's own run."""
+    g = load_golden("config1_k512_d64_256")
+    B, D, H, K = [int(x) for x in g["meta"][:4]]
+    z, embed = seeded_case(B, D, H, H, K, seed=int(g["seed"][0]), kind="gauss")
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H)
+    m = new_vq(K, D, 0.99, flags)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    m.train(True)
+    q, loss, ids = m(z.to(DEV))
+    assert torch.equal(ids.cpu(), t(g["ids_i16"]).long())
+    counts = torch.bincount(ids.reshape(-1), minlength=K).cpu().numpy()
+    assert np.array_equal(counts, g["counts"])
+    assert abs(loss.item() - float(g["loss"][0])) <= TOL * float(g["loss"][0])
+    assert rel_err(m.embed, t(g["embed1"])) <= TOL
+    assert rel_err(m.embed_avg, t(g["embed_avg1"])) <= TOL
+    assert rel_err(m.cluster_size, t(g["cluster_size1"])) <= TOL
+    qs = q.double()
+    assert abs(qs.sum().item() - g["q_checksum"][0]) <= 1e-9 * max(1.0, abs(g["q_checksum"][0])) + 1e-6
+    assert abs(qs.pow(2).sum().item() - g["q_checksum"][1]) <= 1e-9 * g["q_checksum"][1]
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) seeded inputs vs the CPU oracle
+# ---------------------------------------------------------------------------------------------
+SWEEP = [(K, D, kind) for K in (64, 512, 4096) for D in (64, 256) for kind in ("gauss",)] + [
+    (512, 64, "clustered"), (512, 64, "relu"), (512, 256, "relu"), (10, 16, "gauss"), (100, 24, "gauss"),
+    (64, 512, "gauss"), (300, 40, "clustered"), (512, 128, "gauss"), (1000, 96, "relu")]
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("K,D,kind", SWEEP)
+def test_seeded_vs_oracle(K, D, kind, flags):
+    B, H = 2, 64                                   # N = 8192 vectors
+    z, embed = seeded_case(B, D, H, H, K, seed=1234 + K + D, kind=kind)
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H, chunk=8192)
+    m = new_vq(K, D, 0.99, flags)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    ora.train(True)
+    m.train(True)
+    g = torch.Generator().manual_seed(7)
+    g_q = torch.randn(B, D, H, H, generator=g)
+
+    z_ref = z.clone().requires_grad_(True)
+    q_ref, loss_ref, ids_ref = ora(z_ref)
+    (gz_ref,) = torch.autograd.grad((q_ref * g_q).sum() + 0.7 * loss_ref, z_ref)
+
+    z_gpu = z.to(DEV).requires_grad_(True)
+    q, loss, ids = m(z_gpu)
+    (gz,) = torch.autograd.grad((q * g_q.to(DEV)).sum() + 0.7 * loss, z_gpu)
+
+    nties = assert_ids_match(ids, ids_ref, embed, z)
+    if nties == 0:
+        assert torch.equal(q.detach().cpu(), q_ref.detach().contiguous())
+        assert rel_err(m.cluster_size, ora.cluster_size) <= TOL
+        assert rel_err(m.embed_avg, ora.embed_avg) <= TOL
+        assert rel_err(m.embed, ora.embed) <= TOL
+        assert rel_err(gz, gz_ref) <= TOL
+    assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_cold_start_exploded_codes(flags):
+    """First EMA step with cluster_size == 0 blows unused codes up to ~1e5 x;
+    the next forward must still pick the reference's codes."""
+    B, D, H, K = 1, 64, 32, 512                   # N = 1024 < K*... many dead codes
+    z, embed = seeded_case(B, D, H, H, K, seed=31)
+    ora = make_oracle(K, D, embed)
+    m = new_vq(K, D, 0.99, flags)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    ora.train(True)
+    m.train(True)
+    for step in range(3):
+        zz, _ = seeded_case(B, D, H, H, K, seed=100 + step)
+        _, loss_ref, ids_ref = ora(zz)
+        _, loss, ids = m(zz.to(DEV))
+        assert torch.equal(ids.cpu(), ids_ref)
+        assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
+        assert rel_err(m.embed, ora.embed) <= TOL
+        assert ora.embed.abs().max() > 1e4         # the explosion really happened
+        set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("B,D,H,K", [(1, 3, 5, 7), (2, 1, 1, 1), (1, 17, 9, 33), (3, 8, 2, 2), (1, 260, 6, 5)])
+def test_ragged_shapes(B, D, H, K, flags):
+    z, embed = seeded_case(B, D, H, H, K, seed=B * 1000 + D)
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H)
+    m = new_vq(K, D, 0.9, flags)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    ora.train(True)
+    m.train(True)
+    z_ref = z.clone().requires_grad_(True)
+    q_ref, loss_ref, ids_ref = ora(z_ref)
+    (gz_ref,) = torch.autograd.grad(q_ref.sum() * 0.5 + loss_ref, z_ref)
+    z_gpu = z.to(DEV).requires_grad_(True)
+    q, loss, ids = m(z_gpu)
+    (gz,) = torch.autograd.grad(q.sum() * 0.5 + loss, z_gpu)
+    assert torch.equal(ids.cpu(), ids_ref)
+    assert torch.equal(q.detach().cpu(), q_ref.detach().contiguous())
+    assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item()) + 1e-12
+    assert rel_err(gz, gz_ref) <= TOL
+    assert rel_err(m.embed, ora.embed) <= TOL
+
+
+def test_empty_batch():
+    m = new_vq(8, 4)
+    m.train(True)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    q, loss, ids = m(torch.empty(0, 4, 6, 6, device=DEV))
+    assert q.shape == (0, 4, 6, 6) and ids.shape == (0, 6, 6)
+    # EMA with zero counts: cluster_size decays, embed_avg decays (reference arithmetic on an empty batch)
+    assert torch.allclose(m.cluster_size, before["cluster_size"] * 0.99)
+    assert m.lookup(torch.empty(0, 6, 6, dtype=torch.long, device=DEV)).shape == (0, 6, 6, 4)
+
+
+def test_rejects_non_square_and_bad_dtype():
+    m = new_vq(8, 4)
+    with pytest.raises(ValueError, match="square"):
+        m(torch.randn(1, 4, 6, 8, device=DEV))
+    with pytest.raises(TypeError):
+        m(torch.randn(1, 4, 6, 6, device=DEV, dtype=torch.float16))
+    with pytest.raises(ValueError, match="channels"):
+        m(torch.randn(1, 5, 6, 6, device=DEV))
+
+
+def test_duplicate_codes_pick_a_maximiser_lowest_index():
+    """Exact ties: the reference's choice is implementation-defined; ours is the lowest index."""
+    D, K, H = 8, 6, 4
+    g = torch.Generator().manual_seed(5)
+    embed = torch.randn(K, D, generator=g)
+    embed[4] = embed[1]
+    z = embed[torch.tensor([1, 4, 1, 4] * 4)].T.reshape(1, D, H, H).contiguous()
+    m = new_vq(K, D)
+    set_state(m, embed.numpy(), np.zeros(K, np.float32), embed.T.numpy())
+    m.eval()
+    q, loss, ids = m(z.to(DEV))
+    assert bool((ids == 1).all())
+    assert loss.item() == 0.0
+
+
+def test_eval_and_no_grad_semantics():
+    K, D, H = 32, 16, 8
+    z, embed = seeded_case(2, D, H, H, K, seed=9)
+    m = new_vq(K, D)
+    set_state(m, embed.numpy(), np.ones(K, np.float32), embed.T.numpy())
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    m.eval()
+    zg = z.to(DEV).requires_grad_(True)
+    q, loss, ids = m(zg)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), f"eval() must not touch {k}"
+    assert q.requires_grad and loss.requires_grad and not ids.requires_grad
+    ids += 1                                        # callers mutate ids in place (vqwnet.py:111)
+    with torch.no_grad():
+        q2, loss2, ids2 = m(z.to(DEV))
+    assert not q2.requires_grad and not loss2.requires_grad
+    assert torch.equal(ids2 + 1, ids)
+    m.train()
+    with torch.no_grad():
+        m(z.to(DEV))
+    assert not torch.equal(m.cluster_size, before["cluster_size"])   # training updates even under no_grad
+
+
+def test_backward_partial_grads():
+    K, D, H = 32, 16, 8
+    z, embed = seeded_case(2, D, H, H, K, seed=10)
+    ora = make_oracle(K, D, embed)
+    ora.eval()
+    m = new_vq(K, D)
+    set_state(m, embed.numpy(), np.zeros(K, np.float32), embed.T.numpy())
+    m.eval()
+    for use_q, use_loss in ((True, False), (False, True)):
+        zr = z.clone().requires_grad_(True)
+        qr, lr, _ = ora(zr)
+        zg = z.to(DEV).requires_grad_(True)
+        qg, lg, _ = m(zg)
+        obj_r = (qr.pow(2).sum() if use_q else 0) + (3.0 * lr if use_loss else 0)
+        obj_g = (qg.pow(2).sum() if use_q else 0) + (3.0 * lg if use_loss else 0)
+        (gr,) = torch.autograd.grad(obj_r, zr)
+        (gg,) = torch.autograd.grad(obj_g, zg)
+        assert rel_err(gg, gr) <= TOL
+
+
+def test_non_contiguous_input_and_reassigned_codebook():
+    K, D, H = 40, 12, 10
+    z, embed = seeded_case(2, D, H, H, K, seed=12)
+    ora = make_oracle(K, D, embed)
+    ora.eval()
+    m = new_vq(K, D)
+    m.embed = embed.to(DEV)                          # reassignment as in unet_encoder.py:85
+    m.eval()
+    z_nc = z.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)   # channels-last strides
+    assert not z_nc.is_contiguous()
+    q, loss, ids = m(z_nc.to(DEV))
+    q_ref, loss_ref, ids_ref = ora(z)
+    assert torch.equal(ids.cpu(), ids_ref)
+    assert torch.equal(q.cpu(), q_ref.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+# lookup (vq_module.py:203-206) -- pure gather: bit-exact vs F.embedding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,D", [(10, 16), (512, 64), (64, 512), (7, 3), (4096, 256)])
+def test_lookup_matches_embedding(K, D):
+    g = torch.Generator().manual_seed(K + D)
+    embed = torch.randn(K, D, generator=g)
+    m = new_vq(K, D)
+    set_state(m, embed.numpy(), np.zeros(K, np.float32), embed.T.numpy())
+    for shape in ((2, 16, 16), (1, 33, 17), (5,), (3, 7), (2, 3, 4, 5)):
+        ids = torch.randint(0, K, shape, generator=g)
+        out = m.lookup(ids.to(DEV))
+        ref = F.embedding(ids, embed)
+        assert out.shape == ref.shape
+        assert torch.equal(out.cpu(), ref)
+        if len(shape) == 3:
+            # the callers' transpose(1,-1) (unet_encoder.py:120-123) lands on contiguous NCHW memory
+            assert out.transpose(1, -1).is_contiguous()
+            assert torch.equal(out.transpose(1, -1).cpu(), ref.transpose(1, -1))
+
+
+def test_recon_config4_lookup_path():
+    """BASELINE config 4 (run_recon.py:170-192): K=10, D=16, 512x512 label map -> embedding map."""
+    K, D, S = 10, 16, 512
+    g = torch.Generator().manual_seed(4)
+    embed = torch.randn(K, D, generator=g)
+    ids = torch.randint(0, K, (1, S, S), generator=g)
+    m = new_vq(K, D, momentum=0.999)
+    set_state(m, embed.numpy(), np.zeros(K, np.float32), embed.T.numpy())
+    x = m.lookup(torch.transpose(ids.to(DEV), 1, 2)).transpose(1, -1)       # get_embed_from_ids
+    ref = F.embedding(torch.transpose(ids, 1, 2), embed).transpose(1, -1)
+    assert x.shape == (1, D, S, S) and torch.equal(x.cpu(), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) properties at BASELINE's full sizes (config 2 quantiser shape: 16x64x256x256, K=512; N = 1M)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("K,D", [(512, 64), (512, 256), (64, 64)])
+def test_full_size_properties(K, D, flags):
+    B, H = 16, 256
+    N = B * H * H
+    gen = torch.Generator(device=DEV).manual_seed(1234)
+    z = torch.randn(B, D, H, H, device=DEV, generator=gen)
+    embed = torch.randn(K, D, device=DEV, generator=gen)
+    m = new_vq(K, D, 0.99, flags)
+    with torch.no_grad():
+        m.embed.copy_(embed)
+        m.embed_avg.copy_(embed.T)
+        m.cluster_size.fill_(1.0)
+    m.train(True)
+    zg = z.clone().requires_grad_(True)
+    q, loss, ids = m(zg)
+    ids_nat = ids.transpose(1, 2)                                   # [b,h,w]
+    # round trip: q == codebook[ids] (pre-update codebook)
+    q_chk = F.embedding(ids_nat, embed).permute(0, 3, 1, 2)
+    assert torch.equal(q.detach(), q_chk)
+    # every pixel got a code; histogram is exact
+    counts = torch.bincount(ids.reshape(-1), minlength=K)
+    assert int(counts.sum()) == N and int(ids.min()) >= 0 and int(ids.max()) < K
+    # the chosen code is a nearest code: no other code is closer than fp32 noise allows (sampled rows)
+    samp = torch.randint(0, N, (4096,), device=DEV, generator=gen)
+    flat = z.permute(0, 2, 3, 1).reshape(N, D)[samp].double()
+    d = torch.cdist(flat, embed.double())
+    chosen = ids_nat.reshape(-1)[samp]
+    gap = d.gather(1, chosen[:, None]).squeeze(1) - d.min(1).values
+    assert float(gap.max()) <= 1e-4
+    # loss == mean((z-q)^2)
+    ref_loss = (z.double() - q.detach().double()).pow(2).mean().item()
+    assert abs(loss.item() - ref_loss) <= TOL * ref_loss
+    # EMA statistics: cluster_size = 0.99*1 + 0.01*counts ; sum over codes of embed_avg is linear in z
+    cs_ref = 0.99 * 1.0 + (1 - 0.99) * counts.double()
+    assert rel_err(m.cluster_size, cs_ref) <= TOL
+    sums_ref = torch.zeros(K, D, device=DEV, dtype=torch.float64).index_add_(
+        0, ids_nat.reshape(-1), z.permute(0, 2, 3, 1).reshape(N, D).double())
+    avg_ref = 0.99 * embed.double().T + (1 - 0.99) * sums_ref.T
+    assert rel_err(m.embed_avg, avg_ref) <= TOL
+    # backward: g_z = g_q + 2 w (z-q)/numel
+    g_q = torch.randn(B, D, H, H, device=DEV, generator=gen)
+    (gz,) = torch.autograd.grad((q * g_q).sum() + 2.5 * loss, zg)
+    gz_ref = g_q.double() + 2.5 * 2.0 * (z.double() - q.detach().double()) / z.numel()
+    assert rel_err(gz, gz_ref) <= TOL
+    # idempotence: quantising the quantised map returns the same codes and zero loss
+    m.eval()
+    q2, loss2, ids2 = m(q.detach())
+    assert torch.equal(ids2, ids) and loss2.item() == 0.0
+
+
+def test_simt_and_auto_paths_agree_at_full_size():
+    B, D, H, K = 16, 64, 256, 512
+    gen = torch.Generator(device=DEV).manual_seed(99)
+    z = torch.randn(B, D, H, H, device=DEV, generator=gen)
+    embed = torch.randn(K, D, device=DEV, generator=gen)
+    outs = []
+    for flags in (_native.VQ_FLAG_FORCE_SIMT, 0):
+        m = new_vq(K, D, 0.99, flags)
+        with torch.no_grad():
+            m.embed.copy_(embed)
+            m.embed_avg.copy_(embed.T)
+        m.train(True)
+        q, loss, ids = m(z)
+        outs.append((ids, q, loss, m.cluster_size.clone(), m.embed.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert abs(outs[0][2].item() - outs[1][2].item()) <= TOL * outs[0][2].item()
+    assert torch.equal(outs[0][3], outs[1][3])
+    assert rel_err(outs[1][4], outs[0][4]) <= TOL
