@@ -59,10 +59,12 @@ int vq_assign_path(int B, int D, int H, int W, int K, int flags);
 /* Workspace bytes needed by vq_assign_fwd for N = B*H*W vectors. */
 size_t vq_workspace_bytes(int64_t N, int K, int D);
 
-/* Floats in the packed statistics buffer: [cnt_hi K | cnt_lo K | sums K*D]
+/* Floats in the packed statistics buffer: [cnt_hi K | cnt_lo K | pad | sums K*D]
  * (count = cnt_hi*4096 + cnt_lo, both halves stay exactly representable in fp32 under an
- * all-reduce(sum) over <= 4096 ranks). */
+ * all-reduce(sum) over <= 4096 ranks; sums start at vq_stats_sums_offset(K) floats, a multiple
+ * of 4 so that rows of sums are 16-byte aligned whenever D % 4 == 0). */
 size_t vq_stats_floats(int K, int D);
+size_t vq_stats_sums_offset(int K);
 
 /*
  * Nearest-code assignment, gather, commitment loss and (optionally) EMA statistics in one
@@ -77,7 +79,7 @@ size_t vq_stats_floats(int K, int D);
  *   ids_nat  [B,H,W]   int32, natural order (kept for the backward pass); may be NULL
  *   q        [B,D,H,W] contiguous NCHW quantised output; may be NULL
  *   loss     scalar    mean((z-q)^2) over B*D*H*W  (F.mse_loss, vq_module.py:163); may be NULL
- *   stats    packed [cnt_hi K | cnt_lo K | sums K*D] (see vq_stats_floats), sums[k*D+d] =
+ *   stats    packed [cnt_hi K | cnt_lo K | pad | sums K*D] (see vq_stats_floats), sums[k*D+d] =
  *            sum of z over pixels assigned to k (== embed_sum[d,k], vq_module.py:185);
  *            NULL in eval mode
  *   embed_snapshot [K,D] copy of the codebook used for this call (backward needs the
@@ -92,13 +94,18 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W,
 /*
  * EMA codebook update from (possibly all-reduced) packed statistics.  Replaces
  * vq_module.py:194-199 (exponential_moving_average_ x2, Laplace smoothing, embed refresh).
- *   cluster_size [K], embed_avg [D,K], embed [K,D]: the module's three buffers, updated in place
+ *   cluster_size [K], embed_avg [D,K], embed [K,D]: the module's three buffers, updated in place;
+ *   embed_avg is addressed as embed_avg[d*avg_stride_d + k*avg_stride_k] (element strides): the
+ *   reference builds it with `embed.T.clone()` (vq_module.py:156), which keeps the transposed
+ *   strides (1, D), while a checkpoint round-trip may leave it contiguous (K, 1)
+ *   momentum / eps are the Python doubles of the module (the reference forms 1-momentum and
+ *   dict_size*eps in double before they meet the fp32 tensors);
  *   count_scale / sum_scale: multiply counts / sums before the update (1 for a single rank
  *   or global-batch semantics, 1/world_size for the reference's mean semantics)
  *   scratch: >= 16 bytes of device memory
  */
-int vq_ema_update(float* cluster_size, float* embed_avg, float* embed,
-                  const float* stats, int K, int D, float momentum, float eps,
+int vq_ema_update(float* cluster_size, float* embed_avg, int64_t avg_stride_d, int64_t avg_stride_k,
+                  float* embed, const float* stats, int K, int D, double momentum, double eps,
                   float count_scale, float sum_scale, void* scratch, vq_stream_t stream);
 
 /*

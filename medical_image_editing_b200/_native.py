@@ -27,11 +27,13 @@ SIGNATURES = {
     "vq_assign_path": (ctypes.c_int, [ctypes.c_int] * 6),
     "vq_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "vq_stats_floats": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "vq_stats_sums_offset": (ctypes.c_size_t, [ctypes.c_int]),
     "vq_assign_fwd": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      c_f32p, ctypes.c_int, c_i64p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
-    "vq_ema_update": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int,
-                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+    "vq_ema_update": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int64, ctypes.c_int64, c_f32p, c_f32p,
+                                     ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_void_p, ctypes.c_void_p]),
     "vq_bwd": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_f32p,
                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

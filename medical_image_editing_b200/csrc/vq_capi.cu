@@ -11,7 +11,9 @@ int vq_version(void) { return 1000; }
 
 const char* vq_last_error(void) { return get_error(); }
 
-size_t vq_stats_floats(int K, int D) { return (size_t)2 * (size_t)K + (size_t)K * (size_t)D; }
+size_t vq_stats_floats(int K, int D) { return stats_sums_offset(K) + (size_t)K * (size_t)D; }
+
+size_t vq_stats_sums_offset(int K) { return stats_sums_offset(K); }
 
 size_t vq_workspace_bytes(int64_t N, int K, int D) {
   if (N < 0 || K <= 0 || D <= 0) return 0;
@@ -67,13 +69,15 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
   return launch_finish(a, s);
 }
 
-int vq_ema_update(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
-                  float momentum, float eps, float count_scale, float sum_scale, void* scratch, vq_stream_t stream) {
+int vq_ema_update(float* cluster_size, float* embed_avg, int64_t avg_stride_d, int64_t avg_stride_k, float* embed,
+                  const float* stats, int K, int D, double momentum, double eps, float count_scale, float sum_scale,
+                  void* scratch, vq_stream_t stream) {
   set_error("");
   VQ_REQUIRE(K > 0 && D > 0, VQ_ERR_INVALID_ARG, "vq_ema_update: bad shape K=%d D=%d", K, D);
   VQ_REQUIRE(cluster_size && embed_avg && embed && stats && scratch, VQ_ERR_INVALID_ARG, "vq_ema_update: null pointer");
-  return launch_ema(cluster_size, embed_avg, embed, stats, K, D, momentum, eps, count_scale, sum_scale,
-                    (float*)scratch, (cudaStream_t)stream);
+  VQ_REQUIRE(avg_stride_d >= 0 && avg_stride_k >= 0, VQ_ERR_INVALID_ARG, "vq_ema_update: negative embed_avg stride");
+  return launch_ema(cluster_size, embed_avg, avg_stride_d, avg_stride_k, embed, stats, K, D, momentum, eps,
+                    count_scale, sum_scale, (float*)scratch, (cudaStream_t)stream);
 }
 
 int vq_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat, const float* embed_snapshot,

@@ -59,6 +59,7 @@ struct Workspace {
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t stats_sums_offset(int K) { return align_up((size_t)2 * K, 4); }
 inline int pad_codes(int K) { return (int)align_up((size_t)K, kCodePad); }
 inline int tc_dpad(int D) { return (int)align_up((size_t)D + 8, 32); }   // D + 8 augmentation columns
 
@@ -95,8 +96,9 @@ int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s
 int launch_assign_tc(const FwdArgs& a, cudaStream_t s);          // vq_assign_tc.cu
 bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc.cu
 int launch_finish(const FwdArgs& a, cudaStream_t s);
-int launch_ema(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
-               float momentum, float eps, float count_scale, float sum_scale, float* scratch, cudaStream_t s);
+int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,
+               const float* stats, int K, int D, double momentum, double eps, float count_scale, float sum_scale,
+               float* scratch, cudaStream_t s);
 int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat,
                const float* snap, float* g_z, int B, int D, int H, int W, int K, cudaStream_t s);
 int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout,

@@ -356,10 +356,10 @@ vq_ema_cs_kernel(float* __restrict__ cluster_size, const float* __restrict__ sta
 }
 
 __global__ void __launch_bounds__(256)
-vq_ema_embed_kernel(const float* __restrict__ cluster_size, float* __restrict__ embed_avg, float* __restrict__ embed,
-                    const float* __restrict__ sums, int K, int D, float momentum, float alpha, float sum_scale,
-                    float eps, float k_eps, const float* __restrict__ scratch) {
-  // 32x32 tile transpose: embed_avg is [D][K] (k fastest), sums / embed are [K][D] (d fastest)
+vq_ema_embed_kernel(const float* __restrict__ cluster_size, float* __restrict__ embed_avg, long long sd, long long sk,
+                    float* __restrict__ embed, const float* __restrict__ sums, int K, int D, float momentum,
+                    float alpha, float sum_scale, float eps, float k_eps, const float* __restrict__ scratch) {
+  // 32x32 tile transpose: embed_avg addressed [d*sd + k*sk] (coalesced when sk == 1); sums / embed are [K][D]
   __shared__ float t_in[32][33];
   __shared__ float t_out[32][33];
   const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -373,7 +373,7 @@ vq_ema_embed_kernel(const float* __restrict__ cluster_size, float* __restrict__ 
   for (int r = ly; r < 32; r += 8) {            // d = d0 + r, k = k0 + lx
     const int d = d0 + r, k = k0 + lx;
     if (k < K && d < D) {
-      const size_t ia = (size_t)d * K + k;
+      const size_t ia = (size_t)d * sd + (size_t)k * sk;
       const float avg = __fmaf_rn(alpha, t_in[lx][r], __fmul_rn(embed_avg[ia], momentum));
       embed_avg[ia] = avg;
       const float cs = __fdiv_rn(__fmul_rn(n, __fadd_rn(cluster_size[k], eps)), __fadd_rn(n, k_eps));
@@ -384,6 +384,22 @@ vq_ema_embed_kernel(const float* __restrict__ cluster_size, float* __restrict__ 
   for (int r = ly; r < 32; r += 8) {            // write embed[k0+r][d0+lx]
     const int k = k0 + r, d = d0 + lx;
     if (k < K && d < D) embed[(size_t)k * D + d] = t_out[r][lx];
+  }
+}
+
+// embed_avg stored code-major (strides (1, D): what `embed.T.clone()` produces): pure element-wise
+__global__ void __launch_bounds__(256)
+vq_ema_embed_kd_kernel(const float* __restrict__ cluster_size, float* __restrict__ embed_avg, float* __restrict__ embed,
+                       const float* __restrict__ sums, int K, int D, float momentum, float alpha, float sum_scale,
+                       float eps, float k_eps, const float* __restrict__ scratch) {
+  const float n = scratch[0];
+  const size_t tot = (size_t)K * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / D);
+    const float avg = __fmaf_rn(alpha, sums[i] * sum_scale, __fmul_rn(embed_avg[i], momentum));
+    embed_avg[i] = avg;
+    const float cs = __fdiv_rn(__fmul_rn(n, __fadd_rn(cluster_size[k], eps)), __fadd_rn(n, k_eps));
+    embed[i] = __fdiv_rn(avg, cs);
   }
 }
 
@@ -551,7 +567,7 @@ int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s
     blocks = (int)(ntiles < (long long)8 * sm_count() ? ntiles : (long long)8 * sm_count());
   }
   if (blocks < 1) blocks = 1;
-  float* sums = a.stats ? a.stats + 2 * (size_t)a.K : nullptr;
+  float* sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
   const bool prof = !fallback_list_mode && profile_begin(s);
   vq_assign_simt_kernel<<<blocks, 256, 0, s>>>(a.z, a.ws.et, a.ws.e2, a.embed, a.B, a.D, a.H, a.W, a.K, Kpad,
                                                fallback_list_mode ? a.ws.fb_rows : nullptr, a.ws.misc,
@@ -572,16 +588,28 @@ int launch_finish(const FwdArgs& a, cudaStream_t s) {
   return VQ_OK;
 }
 
-int launch_ema(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
-               float momentum, float eps, float count_scale, float sum_scale, float* scratch, cudaStream_t s) {
-  const float alpha = (float)(1.0 - (double)momentum);
-  const float k_eps = (float)((double)K * (double)eps);
+int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,
+               const float* stats, int K, int D, double momentum_d, double eps_d, float count_scale, float sum_scale,
+               float* scratch, cudaStream_t s) {
+  // the reference forms these in Python doubles, then they are cast to fp32 when they meet the tensors
+  const float momentum = (float)momentum_d;
+  const float alpha = (float)(1.0 - momentum_d);              // add_(update, alpha=1 - momentum)
+  const float eps = (float)eps_d;
+  const float k_eps = (float)((double)K * eps_d);             // self.dict_size * self.eps
   vq_ema_cs_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, momentum, alpha, count_scale, scratch);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
-  dim3 grid((K + 31) / 32, (D + 31) / 32);
-  vq_ema_embed_kernel<<<grid, 256, 0, s>>>(cluster_size, embed_avg, embed, stats + 2 * (size_t)K, K, D, momentum,
-                                           alpha, sum_scale, eps, k_eps, scratch);
+  if (avg_sd == 1 && avg_sk == D) {
+    const size_t tot = (size_t)K * D;
+    int blocks = (int)((tot + 255) / 256);
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    vq_ema_embed_kd_kernel<<<blocks, 256, 0, s>>>(cluster_size, embed_avg, embed, stats + stats_sums_offset(K), K, D,
+                                                  momentum, alpha, sum_scale, eps, k_eps, scratch);
+  } else {
+    dim3 grid((K + 31) / 32, (D + 31) / 32);
+    vq_ema_embed_kernel<<<grid, 256, 0, s>>>(cluster_size, embed_avg, avg_sd, avg_sk, embed, stats + stats_sums_offset(K),
+                                             K, D, momentum, alpha, sum_scale, eps, k_eps, scratch);
+  }
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;

@@ -65,7 +65,7 @@ def _all_reduce_stats(stats: torch.Tensor, K: int, reduce_mode: str) -> Tuple[fl
         dist.all_reduce(stats)
         return 1.0 / ws, 1.0 / ws
     if reduce_mode == "reference":      # as written: counts stay rank-local, sums averaged
-        dist.all_reduce(stats[2 * K:])
+        dist.all_reduce(stats[lib().vq_stats_sums_offset(K):])
         return 1.0, 1.0 / ws
     raise ValueError(f"reduce_mode must be one of {REDUCE_MODES}, got {reduce_mode!r}")
 
@@ -120,9 +120,13 @@ class VQFunction(torch.autograd.Function):
                 cscale, sscale = 1.0, 1.0
                 if is_distributed():
                     cscale, sscale = _all_reduce_stats(stats, K, reduce_mode)
-                if not (cluster_size.is_contiguous() and embed_avg.is_contiguous() and embed.is_contiguous()):
-                    raise RuntimeError("B200 VQ: embed / cluster_size / embed_avg buffers must be contiguous")
-                check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), embed.data_ptr(),
+                if not (cluster_size.is_contiguous() and embed.is_contiguous()):
+                    raise RuntimeError("B200 VQ: the embed / cluster_size buffers must be contiguous")
+                if tuple(embed_avg.shape) != (D, K) or tuple(cluster_size.shape) != (K,):
+                    raise RuntimeError("B200 VQ: embed_avg must be [emb_dim, dict_size] and cluster_size [dict_size]")
+                # embed_avg = embed.T.clone() keeps strides (1, D) (vq_module.py:156): pass them through
+                sd, sk = embed_avg.stride()
+                check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), sd, sk, embed.data_ptr(),
                                       stats.data_ptr(), K, D, float(momentum), float(eps), cscale, sscale,
                                       ws.data_ptr(), _stream()), "vq_ema_update")
         if need_bwd:

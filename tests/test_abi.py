@@ -32,6 +32,7 @@ def test_version_and_sizes():
     L = pkg.lib()
     assert L.vq_version() >= 1000
     assert L.vq_stats_floats(512, 64) == 2 * 512 + 512 * 64
+    assert L.vq_stats_sums_offset(5) == 12 and L.vq_stats_floats(5, 4) == 12 + 20
     small = L.vq_workspace_bytes(1024, 512, 64)
     big = L.vq_workspace_bytes(1 << 20, 512, 64)
     assert 0 < small < big
@@ -44,7 +45,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"bad shape" in L.vq_last_error()
     rc = L.vq_lookup(None, 4, None, 0, 16, None, 0, 0, 0, 0, None, None)
     assert rc == -1
-    rc = L.vq_ema_update(None, None, None, None, 8, 8, 0.99, 1e-5, 1.0, 1.0, None, None)
+    rc = L.vq_ema_update(None, None, 1, 8, None, None, 8, 8, 0.99, 1e-5, 1.0, 1.0, None, None)
     assert rc == -1 and b"null" in L.vq_last_error()
 
 

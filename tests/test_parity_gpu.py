@@ -161,7 +161,7 @@ def test_cold_start_exploded_codes(flags):
 @pytest.mark.parametrize("B,D,H,K", [(1, 3, 5, 7), (2, 1, 1, 1), (1, 17, 9, 33), (3, 8, 2, 2), (1, 260, 6, 5)])
 def test_ragged_shapes(B, D, H, K, flags):
     z, embed = seeded_case(B, D, H, H, K, seed=B * 1000 + D)
-    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H)
+    ora = make_oracle(K, D, embed, momentum=0.9, warmed=True, n_for_warm=B * H * H)
     m = new_vq(K, D, 0.9, flags)
     set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
     ora.train(True)
@@ -182,6 +182,8 @@ def test_ragged_shapes(B, D, H, K, flags):
 def test_empty_batch():
     m = new_vq(8, 4)
     m.train(True)
+    with torch.no_grad():
+        m.cluster_size.fill_(2.0)
     before = {k: v.clone() for k, v in m.state_dict().items()}
     q, loss, ids = m(torch.empty(0, 4, 6, 6, device=DEV))
     assert q.shape == (0, 4, 6, 6) and ids.shape == (0, 6, 6)
@@ -356,7 +358,9 @@ def test_full_size_properties(K, D, flags):
     (gz,) = torch.autograd.grad((q * g_q).sum() + 2.5 * loss, zg)
     gz_ref = g_q.double() + 2.5 * 2.0 * (z.double() - q.detach().double()) / z.numel()
     assert rel_err(gz, gz_ref) <= TOL
-    # idempotence: quantising the quantised map returns the same codes and zero loss
+    # idempotence: quantising the quantised map (same codebook) returns the same codes and zero loss
+    with torch.no_grad():
+        m.embed.copy_(embed)
     m.eval()
     q2, loss2, ids2 = m(q.detach())
     assert torch.equal(ids2, ids) and loss2.item() == 0.0
@@ -381,3 +385,25 @@ def test_simt_and_auto_paths_agree_at_full_size():
     assert abs(outs[0][2].item() - outs[1][2].item()) <= TOL * outs[0][2].item()
     assert torch.equal(outs[0][3], outs[1][3])
     assert rel_err(outs[1][4], outs[0][4]) <= TOL
+
+
+def test_embed_avg_layouts():
+    """`embed.T.clone()` (vq_module.py:156) keeps strides (1, D); a checkpoint round trip can make the
+    buffer contiguous.  Both must give the reference's update."""
+    K, D, H = 48, 20, 8
+    z, embed = seeded_case(2, D, H, H, K, seed=44)
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=2 * H * H)
+    ora.train(True)
+    ms = [new_vq(K, D), new_vq(K, D)]
+    assert ms[0].embed_avg.stride() == (1, D)
+    ms[1].embed_avg = ms[1].embed_avg.contiguous()
+    assert ms[1].embed_avg.stride() == (K, 1)
+    for m in ms:
+        set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+        m.train(True)
+    ora(z)
+    for m in ms:
+        m(z.to(DEV))
+        assert rel_err(m.embed_avg, ora.embed_avg) <= TOL
+        assert rel_err(m.embed, ora.embed) <= TOL
+        assert rel_err(m.cluster_size, ora.cluster_size) <= TOL
