@@ -136,6 +136,14 @@ int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D,
  *                       the last read; synchronises on the recorded events, then resets.
  */
 int64_t vq_launch_count(void);
+/* Debug: raw tensor-core accumulators (z.e - |e|^2/2, tf32) of the search kernel.
+ * out is [B*H*W][vq_debug_tc_ncols(D,K)] floats; returns VQ_ERR_UNSUPPORTED when the shape has no
+ * tensor-core path.  vq_debug_fallback_rows: number of rows the last tensor-core vq_assign_fwd on this
+ * workspace routed to the exhaustive fp32 search (reads 4 bytes device->host, synchronises). */
+int vq_debug_tc_ncols(int D, int K);
+int vq_debug_tc_scores(const float* z, int B, int D, int H, int W, const float* embed, int K, float* out,
+                       void* workspace, size_t workspace_bytes, vq_stream_t stream);
+int vq_debug_fallback_rows(const void* workspace, int64_t N, int K, int D, vq_stream_t stream);
 int vq_profile_enable(int on);
 int vq_profile_read(double* total_ms, int* launches);
 

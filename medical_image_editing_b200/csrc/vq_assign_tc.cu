@@ -1,9 +1,653 @@
-// vq_assign_tc.cu -- tcgen05/TMEM/TMA distance + argmin kernel (placeholder until the kernel lands).
+// vq_assign_tc.cu -- tcgen05 / TMEM / TMA nearest-code search with exact fp32 re-rank (sm_100a).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: codebook once (resident in shared memory), then one 128-pixel z tile per
+//               stage, loaded straight from NCHW (pixel-contiguous => MN-major A operand, no flatten copy)
+//   warp 1      MMA issuer: tcgen05.mma kind::tf32, M=128 pixels x N<=256 codes x K=8 per instruction,
+//               fp32 accumulators in TMEM (2 stages x 256 columns); one extra K-step multiplies a block of
+//               ones with a 3-way tf32 split of -|e|^2/2, so the accumulator holds z.e - |e|^2/2 directly
+//   warps 2..5  epilogue, thread = pixel: tcgen05.ld 32 columns at a time, running max (FMNMX3) and a
+//               sign-bit candidate mask against (max - bound) (FADD + SHF); then EXACT fp32 scores of the
+//               surviving candidates in the reference's op order, gather of q, (z-q)^2, EMA statistics.
+//
+// Exactness: tf32 drops 13 mantissa bits of z and e, so an approximate score can be off by at most
+//   b = 2^-8 |z| |e|  (+ accumulation slop).  Every code whose approximate score is within 2b of the
+//   approximate maximum is re-scored in exact fp32 (same fma chain as the CUDA-core kernel), so the
+//   winner is the fp32 winner.  Rows with more candidates than the kernel keeps, non-finite rows, or rows
+//   where a norm-outlier ("exploded") code could still win are appended to a list that the CUDA-core
+//   kernel then searches exhaustively.  Nothing is probabilistic.
+#include <cuda.h>
+#include <math.h>
+
 #include "vq_common.cuh"
+
 namespace vqb200 {
-bool tc_path_supported(int, int, int, int, int) { return false; }
-int launch_assign_tc(const FwdArgs&, cudaStream_t) {
-  set_error("tensor-core path not built");
-  return VQ_ERR_UNSUPPORTED;
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_TILE = 128;        // pixels per tile (UMMA M)
+constexpr int TC_MAXBN = 256;       // codes per accumulator stage (UMMA N)
+constexpr int TC_DCH = 32;          // channels per shared-memory chunk (128-byte swizzle rows)
+constexpr int TC_THREADS = 192;     // producer warp, MMA warp, 4 epilogue warps
+constexpr int TC_CL = 4;            // candidate records per pixel
+constexpr int TC_CMAX = 8;          // candidates re-scored per pixel before falling back
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+struct TcGeom {
+  int BN, nb, nD, nst;
+  size_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_bar, total;
+  bool ok;
+};
+
+static TcGeom tc_geometry(int D, int K) {
+  TcGeom g{};
+  g.ok = false;
+  g.BN = K > 128 ? 256 : (int)align_up((size_t)K, 32);
+  g.nb = (K + g.BN - 1) / g.BN;
+  g.nD = (D + TC_DCH - 1) / TC_DCH;
+  const size_t emain = (size_t)g.nb * g.nD * g.BN * 128;
+  const size_t eaug = (size_t)g.nb * g.BN * 32;
+  const size_t zstage = (size_t)g.nD * TC_TILE * 128;
+  size_t off = 0;
+  g.off_emain = off; off += emain;
+  g.off_eaug = off;  off += align_up(eaug, 1024);
+  g.off_aaug = off;  off += 4096;
+  g.off_z = off;
+  const size_t tail = (size_t)2 * TC_CL * TC_TILE * 4 + align_up((size_t)K * 4, 16) + 256;
+  for (int nst = 2; nst >= 1; --nst) {
+    if (off + nst * zstage + tail + 1024 <= (size_t)TC_SMEM_LIMIT) { g.nst = nst; g.ok = true; break; }
+  }
+  if (!g.ok) return g;
+  off += g.nst * zstage;
+  g.off_rec = off;  off += (size_t)2 * TC_CL * TC_TILE * 4;
+  g.off_hist = off; off += align_up((size_t)K * 4, 16);
+  g.off_bar = off;  off += 256;
+  g.total = off + 1024;   // slack for manual 1024-byte alignment of the dynamic smem base
+  return g;
 }
+
+bool tc_path_supported(int B, int D, int H, int W, int K) {
+  const long long HW = (long long)H * W;
+  if (B <= 0 || HW <= 0) return false;
+  if (HW % TC_TILE != 0) return false;          // tiles never straddle images; TMA strides need HW % 4 == 0
+  if (D % 4 != 0 || D < 4) return false;        // 16-byte rows for TMA / float4 gathers
+  if (K < 1) return false;
+  return tc_geometry(D, K).ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)(layout & 7) << 61;      // 0 = no swizzle, 1 = 128 B swizzle / 32 B atom, 2 = 128 B swizzle
+  return d;
+}
+// instruction descriptor: tf32 x tf32 -> f32, A MN-major (pixels contiguous), B K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                  // c_format  = F32
+  d |= 2u << 7;                  // a_format  = TF32
+  d |= 2u << 10;                 // b_format  = TF32
+  d |= 1u << 15;                 // a_major   = MN
+  d |= 0u << 16;                 // b_major   = K
+  d |= (uint32_t)(n >> 3) << 17; // N
+  d |= (uint32_t)(128 >> 4) << 24;  // M
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// prep 2 (single CTA): norm statistics, bounds, and the shared-memory image of the augmentation columns
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// meta[0] = R_live (largest norm of a code taking part in the approximate search, rounded up)
+// meta[1] = r_minbig (smallest norm of an excluded "big" code, rounded down; +inf if none)
+// meta[2] = c1, meta[3] = c2  (error-bound coefficients, see tc_row_bound)
+__global__ void __launch_bounds__(1024)
+vq_tc_prep2_kernel(const float* __restrict__ e2, int K, int D, int BN, int nb, float* __restrict__ eaug_img,
+                   float* __restrict__ meta) {
+  __shared__ int hist[256];
+  __shared__ float s_rcap;
+  __shared__ float red_max[32], red_min[32];
+  const int tid = threadIdx.x;
+  if (tid < 256) hist[tid] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) {
+    const float r = sqrtf(e2[k]);
+    atomicAdd(&hist[(__float_as_uint(r) >> 23) & 0xFF], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cum = 0, emed = 0;
+    for (int e = 0; e < 256; ++e) { cum += hist[e]; if (2 * cum >= K) { emed = e; break; } }
+    // 8 x the lower edge of the median exponent bin (>= 4 x every norm in that bin)
+    int ecap = emed + 3;
+    if (ecap > 254) ecap = 254;
+    s_rcap = __uint_as_float((uint32_t)ecap << 23);
+  }
+  __syncthreads();
+  const float rcap = s_rcap;
+  float rl = 0.f, rb = INFINITY;
+  for (int k = tid; k < K; k += blockDim.x) {
+    const float r = sqrtf(e2[k]);
+    if (r <= rcap) rl = fmaxf(rl, r); else rb = fminf(rb, r);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+    rb = fminf(rb, __shfl_xor_sync(0xffffffffu, rb, o));
+  }
+  if ((tid & 31) == 0) { red_max[tid >> 5] = rl; red_min[tid >> 5] = rb; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { rl = fmaxf(rl, red_max[i]); rb = fminf(rb, red_min[i]); }
+    const float slop = (float)D * 1.2e-7f + 1e-5f;            // |e| computed in fp32 from a rounded |e|^2
+    meta[0] = rl * (1.f + slop);
+    meta[1] = rb * (1.f - slop);
+    meta[2] = 0.00390625f * 1.03f;                            // 2^-8: both operands truncated to tf32
+    meta[3] = (float)(D + 16) * 4.76837158e-7f;               // (D+16) 2^-21: fp32 accumulation in the tensor core
+  }
+  // augmentation image: per group of 8 codes 256 B = [k-half 0: 8 rows x 16 B][k-half 1: 8 rows x 16 B]
+  const int ktot = nb * BN;
+  for (int k = tid; k < ktot; k += blockDim.x) {
+    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;                     // padding / excluded codes never win
+    if (k < K) {
+      const float ee = e2[k];
+      if (sqrtf(ee) <= rcap) {
+        const float x = -0.5f * ee;
+        a0 = tf32_trunc(x);
+        const float r1 = x - a0;
+        a1 = tf32_trunc(r1);
+        a2 = tf32_trunc(r1 - a1);
+      }
+    }
+    const int blk = k / BN, r = k % BN, grp = r >> 3, row = r & 7;
+    float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
+    base[0] = a0; base[1] = a1; base[2] = a2; base[3] = 0.f;
+    base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  const float* z; const float* E; const float* e2; const float* eaug_img; const float* meta;
+  int B, D, H, W, HW, K;
+  int BN, nb, nD, nst;
+  int tiles_per_img; int ntiles;
+  uint32_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_bar;
+  int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts; float* sums;
+  int* fb_count; int* fb_rows;
+  float* dbg;      // optional [N][nb*BN] dump of the raw accumulators
+};
+
+// byte offset of z(p, d) inside a z stage: chunk (d/32) -> group (p/32) -> row (d%32) of 128 B -> 32-byte atom
+// ((p%32)/8) XOR (row%4).  tf32 MN-major operands only exist in the "128-byte swizzle, 32-byte atom" layout
+// (UMMA layout type 1 / CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); the plain 128-byte swizzle silently yields zeros.
+__device__ __forceinline__ uint32_t zs_off(int p, int d) {
+  const int row = d & 31;
+  return (uint32_t)((d >> 5) * (TC_TILE * 128) + (p >> 5) * 4096 + row * 128 +
+                    ((((p & 31) >> 2) ^ ((row & 3) << 1)) << 4) + ((p & 3) << 2));
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint64_t* bars = (uint64_t*)(smem + P.off_bar);
+  const uint32_t bar0 = sbase + P.off_bar;
+  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty ; slot 9: tmem base
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  int* hist = (int*)(smem + P.off_hist);
+
+  const uint32_t zstage_bytes = (uint32_t)P.nD * TC_TILE * 128;
+
+  if (threadIdx.x == 32) {
+    mbar_init(BAR(0), 1);
+    mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
+    mbar_init(BAR(3), 4); mbar_init(BAR(4), 4);
+    mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
+    mbar_init(BAR(7), 4); mbar_init(BAR(8), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    // ones block of the augmentation K-step: 4 groups x 8 rows x 128 B; rows 0..2 = 1, rows 3..7 = 0
+    const int t = threadIdx.x - 64;                       // 0..127
+    float4* a = (float4*)(smem + P.off_aaug);
+    for (int i = t; i < 256; i += 128) {                  // 256 float4 = 4 KB
+      const int row = (i >> 3) & 7;
+      const float v = row < 3 ? 1.f : 0.f;
+      a[i] = make_float4(v, v, v, v);
+    }
+    for (int k = t; k < P.K; k += 128) hist[k] = 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      const uint32_t ebytes = (uint32_t)P.nb * P.nD * P.BN * 128 + (uint32_t)P.nb * P.BN * 32;
+      mbar_expect_tx(BAR(0), ebytes);
+      for (int blk = 0; blk < P.nb; ++blk)
+        for (int c = 0; c < P.nD; ++c)
+          tma_load_2d(sbase + P.off_emain + (uint32_t)(blk * P.nD + c) * P.BN * 128, &emap, BAR(0), c * TC_DCH, blk * P.BN);
+      bulk_load_1d(sbase + P.off_eaug, P.eaug_img, (uint32_t)P.nb * P.BN * 32, BAR(0));
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int s = it % P.nst, ph = (it / P.nst) & 1;
+        mbar_wait(BAR(3 + s), ph ^ 1);
+        mbar_expect_tx(BAR(1 + s), zstage_bytes);
+        const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
+        for (int c = 0; c < P.nD; ++c)
+          for (int grp = 0; grp < 4; ++grp)    // one 32-pixel x 32-channel box per swizzle atom column
+            tma_load_3d(sbase + P.off_z + s * zstage_bytes + c * (TC_TILE * 128) + grp * 4096, &zmap, BAR(1 + s),
+                        pt * TC_TILE + grp * 32, c * TC_DCH, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(P.BN);
+      mbar_wait(BAR(0), 0);
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % P.nst, ph = (it / P.nst) & 1;
+        mbar_wait(BAR(1 + s), ph);
+        tc_fence_after();
+        const uint32_t zaddr = sbase + P.off_z + s * zstage_bytes;
+        for (int blk = 0; blk < P.nb; ++blk, ++g) {
+          const int a = g & 1, aph = (g >> 1) & 1;
+          mbar_wait(BAR(7 + a), aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
+          uint32_t acc = 0;
+          for (int c = 0; c < P.nD; ++c) {
+            const int ksteps = min(4, (P.D - c * TC_DCH + 7) >> 3);
+            const uint32_t eaddr = sbase + P.off_emain + (uint32_t)(blk * P.nD + c) * P.BN * 128;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = make_desc(zaddr + c * (TC_TILE * 128) + ks * 1024, 4096, 512, 1);
+              const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
+              umma_tf32(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+            }
+          }
+          {   // augmentation K-step: ones x (-|e|^2/2 split in three tf32 pieces)
+            const uint64_t ad = make_desc(sbase + P.off_aaug, 1024, 512, 1);
+            const uint64_t bd = make_desc(sbase + P.off_eaug + (uint32_t)blk * P.BN * 32, 128, 256, 0);
+            umma_tf32(d_tmem, ad, bd, idesc, acc);
+          }
+          umma_commit(BAR(5 + a));
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quad = warp & 3;
+    const int p = quad * 32 + lane;                       // pixel within the tile == TMEM lane
+    int* rec_c = (int*)(smem + P.off_rec);                // [TC_CL][128]
+    uint32_t* rec_m = (uint32_t*)(smem + P.off_rec + TC_CL * TC_TILE * 4);
+    const float R = P.meta[0], rminbig = P.meta[1], c1 = P.meta[2], c2 = P.meta[3];
+    const int nchunks = P.BN >> 5;
+    const int ncols = P.nb * P.BN;
+    float lsum = 0.f;
+    int g = 0;
+    mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it % P.nst, ph = (it / P.nst) & 1;
+      const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
+      const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
+      mbar_wait(BAR(1 + s), ph);
+      // |z|^2 (same fma chain as the CUDA-core kernel) and the row's error bound
+      float z2 = 0.f;
+      for (int d = 0; d < P.D; ++d) {
+        const float v = *(const float*)(zs + zs_off(p, d));
+        z2 = __fmaf_rn(v, v, z2);
+      }
+      if (DBG) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
+        float* o2 = P.dbg + (size_t)P.B * P.HW * ncols + ((size_t)b * P.HW + p0 + p) * 8;
+        const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
+        o2[0] = z2;
+        o2[1] = *(const float*)(zs + zs_off(p, 0));
+        o2[2] = *(const float*)(zs + zs_off(p, 1));
+        o2[3] = *(const float*)(eb0 + ((0 ^ (p & 7)) << 4));                             // E[p][0]
+        o2[4] = *(const float*)(eb0 + ((1 ^ (p & 7)) << 4) + 4);                         // E[p][5]
+        o2[5] = *(const float*)(smem + P.off_eaug + (p >> 3) * 256 + (p & 7) * 16);      // aug[p][0]
+        o2[6] = *(const float*)(smem + P.off_aaug + p * 4);
+        o2[7] = __uint_as_float(tmem_base);
+      }
+      const bool bad = !(z2 <= 3.0e38f);
+      const float zn = sqrtf(z2) * 1.00001f;
+      const float bS = c1 * zn * R + c2 * R * (zn + R) + 1e-30f;   // |approx - exact| of S = 2*acc; acc threshold = bS
+      float M = -INFINITY;
+      int cnt = 0;
+      for (int blk = 0; blk < P.nb; ++blk, ++g) {
+        const int a = g & 1, aph = (g >> 1) & 1;
+        mbar_wait(BAR(5 + a), aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
+        float v[32];
+        for (int c = 0; c < nchunks; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (DBG) {
+            float* o = P.dbg + ((size_t)b * P.HW + p0 + p) * ncols + blk * P.BN + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = v[j];
+          }
+          float cm = v[0];
+#pragma unroll
+          for (int j = 1; j < 31; j += 2) cm = fmaxf(fmaxf(cm, v[j]), v[j + 1]);
+          cm = fmaxf(cm, v[31]);
+          if (cm - bS > M) cnt = 0;                       // everything recorded so far is out of range
+          M = fmaxf(M, cm);
+          const float T = M - bS;
+          uint32_t nm = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) nm = __funnelshift_l(__float_as_uint(v[j] - T), nm, 1);
+          const uint32_t cand = ~nm;                      // bit (31-j) set <=> column j is within the bound
+          if (cand) {
+            if (cnt < TC_CL) { rec_c[cnt * TC_TILE + p] = blk * P.BN + c * 32; rec_m[cnt * TC_TILE + p] = cand; }
+            ++cnt;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(7 + a));
+      }
+
+      // ---- exact stage ----------------------------------------------------------------------
+      int total = 0;
+      const int nrec = min(cnt, TC_CL);
+      for (int r = 0; r < nrec; ++r) total += __popc(rec_m[r * TC_TILE + p]);
+      const float lbest = 2.f * M - bS;
+      // excluded ("big") codes: s_k <= r_k (2|z| - r_k), decreasing in r_k for r_k >= |z|
+      bool big_safe = true;
+      if (rminbig < 3.0e38f) {
+        const float bigub = rminbig * (2.f * zn - rminbig);
+        big_safe = (rminbig >= zn) && (bigub + 1e-5f * (fabsf(bigub) + fabsf(lbest)) < lbest);
+      }
+      const bool fb = bad || cnt > TC_CL || total == 0 || total > TC_CMAX || !big_safe;
+      const long long n = (long long)b * P.HW + p0 + p;
+      if (fb) {
+        const int slot = atomicAdd(P.fb_count, 1);
+        P.fb_rows[slot] = (int)n;
+      } else {
+        int w = -1;
+        if (total == 1) {
+          w = rec_c[p] + __clz(rec_m[p]);
+        } else {
+          float best = -INFINITY;
+          for (int r = 0; r < nrec; ++r) {
+            uint32_t m = rec_m[r * TC_TILE + p];
+            const int cbase = rec_c[r * TC_TILE + p];
+            while (m) {
+              const int j = __clz(m);
+              m &= ~(0x80000000u >> j);
+              const int k = cbase + j;
+              // exact fp32 score, reference op order (vq_module.py:54-57), ascending-d fma chain
+              const int blk = k / P.BN, row = k % P.BN;
+              const uint8_t* eb = smem + P.off_emain + (size_t)(blk * P.nD) * P.BN * 128 + row * 128;
+              float dot = 0.f;
+              for (int d = 0; d < P.D; d += 4) {
+                const float4 e4 = *(const float4*)(eb + (size_t)(d >> 5) * P.BN * 128 + ((((d & 31) >> 2) ^ (row & 7)) << 4));
+                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d)), e4.x, dot);
+                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 1)), e4.y, dot);
+                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 2)), e4.z, dot);
+                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 3)), e4.w, dot);
+              }
+              const float sc = ref_score(dot, __ldg(P.e2 + k), z2);
+              if (sc > best || w < 0) { best = sc; w = k; }   // ascending k + strict '>' keeps the lowest index
+            }
+          }
+        }
+        // ---- outputs for the winner: ids, q, (z-q)^2, EMA statistics --------------------------
+        const int pp = p0 + p;
+        const int h = pp / P.W, wc = pp % P.W;
+        if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = w;
+        if (P.ids_nat) P.ids_nat[n] = w;
+        if (P.counts) atomicAdd(&hist[w], 1);
+        const int blk = w / P.BN, row = w % P.BN;
+        const uint8_t* eb = smem + P.off_emain + (size_t)(blk * P.nD) * P.BN * 128 + row * 128;
+        float* qo = P.q ? P.q + ((long long)b * P.D) * P.HW + pp : nullptr;
+        float* so = P.sums ? P.sums + (size_t)w * P.D : nullptr;
+        for (int d = 0; d < P.D; d += 4) {
+          const float4 e4 = *(const float4*)(eb + (size_t)(d >> 5) * P.BN * 128 + ((((d & 31) >> 2) ^ (row & 7)) << 4));
+          const float z0 = *(const float*)(zs + zs_off(p, d));
+          const float z1 = *(const float*)(zs + zs_off(p, d + 1));
+          const float z2v = *(const float*)(zs + zs_off(p, d + 2));
+          const float z3 = *(const float*)(zs + zs_off(p, d + 3));
+          float df = z0 - e4.x; lsum = __fmaf_rn(df, df, lsum);
+          df = z1 - e4.y; lsum = __fmaf_rn(df, df, lsum);
+          df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
+          df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
+          if (qo) {
+            qo[(long long)d * P.HW] = e4.x;
+            qo[(long long)(d + 1) * P.HW] = e4.y;
+            qo[(long long)(d + 2) * P.HW] = e4.z;
+            qo[(long long)(d + 3) * P.HW] = e4.w;
+          }
+          if (so) atomicAdd(reinterpret_cast<float4*>(so + d), make_float4(z0, z1, z2v, z3));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(3 + s));             // z stage free
+    }
+    // ---- per-CTA reductions ------------------------------------------------------------------
+    lsum = warp_sum(lsum);
+    if (lane == 0 && P.loss_acc) atomicAdd(P.loss_acc, (double)lsum);
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+    if (P.counts) {
+      for (int k = threadIdx.x - 64; k < P.K; k += 128) {
+        const int c = hist[k];
+        if (c) atomicAdd(&P.counts[k], c);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int sm_count_tc() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
+  const int HW = a.H * a.W;
+  const TcGeom g = tc_geometry(a.D, a.K);
+  VQ_REQUIRE(g.ok && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
+  EncodeTiledFn enc = get_encode_fn();
+  VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
+             "tensor-core path: z / embed must be 16-byte aligned");
+
+  CUtensorMap zmap, emap;
+  {   // z [B][D][HW]: dim0 = pixel (contiguous), dim1 = channel, dim2 = image; box = 32 pixels x 32 channels
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
+    cuuint32_t box[3] = {32, TC_DCH, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
+  }
+  {   // codebook [K][D] row-major: dim0 = channel, dim1 = code; out-of-range rows / columns read as zero
+    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)a.K};
+    cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
+    cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.embed, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
+  }
+
+  float* eaug_img = a.ws.tc_e;
+  float* meta = a.ws.tc_meta;
+  vq_tc_prep2_kernel<<<1, 1024, 0, s>>>(a.ws.e2, a.K, a.D, g.BN, g.nb, eaug_img, meta);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+
+  TcParams P{};
+  P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
+  P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
+  P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nst = g.nst;
+  P.tiles_per_img = HW / TC_TILE;
+  P.ntiles = a.B * P.tiles_per_img;
+  P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;
+  P.off_z = (uint32_t)g.off_z; P.off_rec = (uint32_t)g.off_rec; P.off_hist = (uint32_t)g.off_hist;
+  P.off_bar = (uint32_t)g.off_bar;
+  P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
+  P.counts = a.stats ? a.ws.counts : nullptr;
+  P.sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
+  P.fb_count = a.ws.misc; P.fb_rows = a.ws.fb_rows;
+  P.dbg = dbg;
+
+  int grid = sm_count_tc();
+  if (grid > P.ntiles) grid = P.ntiles;
+  auto kern = dbg ? vq_assign_tc_kernel<true> : vq_assign_tc_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[dbg ? 1 : 0]) {
+    VQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_set[dbg ? 1 : 0] = true;
+  }
+  const bool prof = profile_begin(s);
+  kern<<<grid, TC_THREADS, g.total, s>>>(zmap, emap, P);
+  if (prof) profile_end(s);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_assign_tc(const FwdArgs& a, cudaStream_t s) { return launch_assign_tc_impl(a, nullptr, s); }
+
+int tc_debug_ncols(int D, int K) {
+  const TcGeom g = tc_geometry(D, K);
+  return g.ok ? g.nb * g.BN : 0;
+}
+
 }  // namespace vqb200

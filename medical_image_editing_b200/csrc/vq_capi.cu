@@ -102,6 +102,32 @@ int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, f
   return launch_lookup(ids, n, embed, K, D, out, layout, B, A, C, status, (cudaStream_t)stream);
 }
 
+int vq_debug_tc_ncols(int D, int K) { return tc_debug_ncols(D, K); }
+
+int vq_debug_tc_scores(const float* z, int B, int D, int H, int W, const float* embed, int K, float* out,
+                       void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(z && embed && out && workspace, VQ_ERR_INVALID_ARG, "vq_debug_tc_scores: null pointer");
+  VQ_REQUIRE(tc_path_supported(B, D, H, W, K), VQ_ERR_UNSUPPORTED, "vq_debug_tc_scores: no tensor-core path for this shape");
+  const int64_t N = (int64_t)B * H * W;
+  VQ_REQUIRE(workspace_bytes >= vq_workspace_bytes(N, K, D), VQ_ERR_WORKSPACE, "vq_debug_tc_scores: workspace too small");
+  FwdArgs a{};
+  a.z = z; a.B = B; a.D = D; a.H = H; a.W = W; a.embed = embed; a.K = K;
+  a.ws = carve_workspace(workspace, N, K, D);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_prep(a, true, s);
+  if (rc) return rc;
+  return launch_assign_tc_impl(a, out, s);
+}
+
+int vq_debug_fallback_rows(const void* workspace, int64_t N, int K, int D, vq_stream_t stream) {
+  Workspace w = carve_workspace((void*)workspace, N, K, D);
+  int v = -1;
+  if (cudaMemcpyAsync(&v, w.misc, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  return v;
+}
+
 int64_t vq_launch_count(void) { return (int64_t)launch_count(); }
 
 int vq_profile_enable(int on) {
