@@ -33,10 +33,11 @@ constexpr int TC_THREADS = 192;     // producer warp, MMA warp, 4 epilogue warps
 constexpr int TC_CL = 4;            // candidate records per pixel
 constexpr int TC_CMAX = 8;          // candidates re-scored per pixel before falling back
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_SORT_MAX = 4096;     // codes the single-CTA sort of vq_tc_prep2_kernel handles
 
 struct TcGeom {
   int BN, nb, nD, nst;
-  size_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_bar, total;
+  size_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_ctab, off_bar, total;
   bool ok;
 };
 
@@ -54,7 +55,8 @@ static TcGeom tc_geometry(int D, int K) {
   g.off_eaug = off;  off += align_up(eaug, 1024);
   g.off_aaug = off;  off += 4096;
   g.off_z = off;
-  const size_t tail = (size_t)2 * TC_CL * TC_TILE * 4 + align_up((size_t)K * 4, 16) + 256;
+  const size_t ctab_bytes = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
+  const size_t tail = (size_t)2 * TC_CL * TC_TILE * 4 + align_up((size_t)K * 4, 16) + ctab_bytes + 256;
   for (int nst = 2; nst >= 1; --nst) {
     if (off + nst * zstage + tail + 1024 <= (size_t)TC_SMEM_LIMIT) { g.nst = nst; g.ok = true; break; }
   }
@@ -62,6 +64,7 @@ static TcGeom tc_geometry(int D, int K) {
   off += g.nst * zstage;
   g.off_rec = off;  off += (size_t)2 * TC_CL * TC_TILE * 4;
   g.off_hist = off; off += align_up((size_t)K * 4, 16);
+  g.off_ctab = off; off += ctab_bytes;
   g.off_bar = off;  off += 256;
   g.total = off + 1024;   // slack for manual 1024-byte alignment of the dynamic smem base
   return g;
@@ -73,7 +76,8 @@ bool tc_path_supported(int B, int D, int H, int W, int K) {
   if (HW % TC_TILE != 0) return false;          // tiles never straddle images; TMA strides need HW % 4 == 0
   if (D % 4 != 0 || D < 4) return false;        // 16-byte rows for TMA / float4 gathers
   if (K < 1) return false;
-  return tc_geometry(D, K).ok;
+  const TcGeom g = tc_geometry(D, K);
+  return g.ok && g.nb * g.BN <= TC_SORT_MAX;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,6 +105,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// polling wait with nanosleep back-off: used by the single-thread producer / MMA roles so that their spinning
+// does not steal issue slots from the epilogue warps sharing the same SM sub-partition
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+  }
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -174,74 +203,124 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
-// prep 2 (single CTA): norm statistics, bounds, and the shared-memory image of the augmentation columns
+// prep 2 (single CTA): sort the codebook by norm, per-chunk error-bound tables, augmentation image
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// meta[0] = R_live (largest norm of a code taking part in the approximate search, rounded up)
-// meta[1] = r_minbig (smallest norm of an excluded "big" code, rounded down; +inf if none)
-// meta[2] = c1, meta[3] = c2  (error-bound coefficients, see tc_row_bound)
+// Codes are laid out in ascending-norm order so that the 32 codes of one scan chunk have similar norms: the
+// approximate-score error of code k is bounded by (c1 |z| |e_k| + c2 |e_k| (|z| + |e_k|)) / 2, and the scan uses
+// one bound per chunk (largest norm in the chunk).  Codes whose norm exceeds 64x the lower edge of the median
+// exponent bin ("big": the exploded dead codes of EMA training) are excluded from the
+// approximate search (augmentation = -1e30) and handled by a rigorous per-row test in the main kernel.
+//   ctab[c] = (A_c, B_c):  bound_c(|z|) = |z| * A_c + B_c        (accumulator units)
+//   meta[1] = r_minbig (smallest norm of an excluded code, rounded down; +inf if none)
 __global__ void __launch_bounds__(1024)
-vq_tc_prep2_kernel(const float* __restrict__ e2, int K, int D, int BN, int nb, float* __restrict__ eaug_img,
-                   float* __restrict__ meta) {
+vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, int K, int D, int BN, int nb,
+                   float* __restrict__ es, float* __restrict__ eaug_img, int* __restrict__ perm,
+                   float* __restrict__ ctab, float* __restrict__ meta) {
+  __shared__ unsigned long long keys[TC_SORT_MAX];
   __shared__ int hist[256];
   __shared__ float s_rcap;
-  __shared__ float red_max[32], red_min[32];
+  __shared__ float red_min[32];
   const int tid = threadIdx.x;
+  const int ktot = nb * BN;
+  int npow = 1;
+  while (npow < ktot) npow <<= 1;
   if (tid < 256) hist[tid] = 0;
   __syncthreads();
-  for (int k = tid; k < K; k += blockDim.x) {
-    const float r = sqrtf(e2[k]);
-    atomicAdd(&hist[(__float_as_uint(r) >> 23) & 0xFF], 1);
+  for (int k = tid; k < npow; k += blockDim.x) {
+    unsigned long long key = ~0ull;                             // padding sorts last
+    if (k < K) {
+      const float r = sqrtf(e2[k]);
+      atomicAdd(&hist[(__float_as_uint(r) >> 23) & 0xFF], 1);
+      uint32_t rb = __float_as_uint(r);
+      if (!(r >= 0.f)) rb = 0x7F800000u;                        // NaN norms sort with +inf
+      key = ((unsigned long long)rb << 32) | (uint32_t)k;
+    }
+    keys[k] = key;
   }
   __syncthreads();
   if (tid == 0) {
     int cum = 0, emed = 0;
     for (int e = 0; e < 256; ++e) { cum += hist[e]; if (2 * cum >= K) { emed = e; break; } }
-    // 8 x the lower edge of the median exponent bin (>= 4 x every norm in that bin)
-    int ecap = emed + 3;
+    int ecap = emed + 6;                                        // 64 x the lower edge of the median exponent bin
     if (ecap > 254) ecap = 254;
     s_rcap = __uint_as_float((uint32_t)ecap << 23);
   }
+  // bitonic sort, ascending (norm, original index)
+  for (int size = 2; size <= npow; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < npow; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const unsigned long long a = keys[i], b = keys[j];
+          const bool up = (i & size) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[j] = a; }
+        }
+      }
+    }
+  }
   __syncthreads();
   const float rcap = s_rcap;
-  float rl = 0.f, rb = INFINITY;
-  for (int k = tid; k < K; k += blockDim.x) {
-    const float r = sqrtf(e2[k]);
-    if (r <= rcap) rl = fmaxf(rl, r); else rb = fminf(rb, r);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
-    rb = fminf(rb, __shfl_xor_sync(0xffffffffu, rb, o));
-  }
-  if ((tid & 31) == 0) { red_max[tid >> 5] = rl; red_min[tid >> 5] = rb; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { rl = fmaxf(rl, red_max[i]); rb = fminf(rb, red_min[i]); }
-    const float slop = (float)D * 1.2e-7f + 1e-5f;            // |e| computed in fp32 from a rounded |e|^2
-    meta[0] = rl * (1.f + slop);
-    meta[1] = rb * (1.f - slop);
-    meta[2] = 0.00390625f * 1.03f;                            // 2^-8: both operands truncated to tf32
-    meta[3] = (float)(D + 16) * 4.76837158e-7f;               // (D+16) 2^-21: fp32 accumulation in the tensor core
-  }
-  // augmentation image: per group of 8 codes 256 B = [k-half 0: 8 rows x 16 B][k-half 1: 8 rows x 16 B]
-  const int ktot = nb * BN;
-  for (int k = tid; k < ktot; k += blockDim.x) {
-    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;                     // padding / excluded codes never win
-    if (k < K) {
-      const float ee = e2[k];
-      if (sqrtf(ee) <= rcap) {
-        const float x = -0.5f * ee;
+  const float c1 = 0.00390625f * 1.03f;                         // 2^-8: z and e both truncated to tf32 (score units)
+  const float c2 = (float)(D + 16) * 4.76837158e-7f;            // (D+16) 2^-21: fp32 accumulation in the tensor core
+  const float slop = 1.f + (float)D * 1.2e-7f + 1e-5f;          // |e| was computed in fp32 from a rounded |e|^2
+  // per sorted position: perm, augmentation image
+  float rb = INFINITY;
+  for (int i = tid; i < ktot; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    const int k = (int)(uint32_t)key;
+    const float r = __uint_as_float((uint32_t)(key >> 32));
+    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;                      // padding / excluded codes never win
+    const bool real = key != ~0ull;
+    perm[i] = real ? k : 0;
+    if (real) {
+      if (r <= rcap) {
+        const float x = -0.5f * e2[k];
         a0 = tf32_trunc(x);
         const float r1 = x - a0;
         a1 = tf32_trunc(r1);
         a2 = tf32_trunc(r1 - a1);
+      } else {
+        rb = fminf(rb, r);
       }
     }
-    const int blk = k / BN, r = k % BN, grp = r >> 3, row = r & 7;
+    const int blk = i / BN, rr = i % BN, grp = rr >> 3, row = rr & 7;
     float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
     base[0] = a0; base[1] = a1; base[2] = a2; base[3] = 0.f;
     base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
+  }
+  // per 32-code chunk: largest live norm -> bound coefficients (accumulator units = score units / 2)
+  for (int c = tid; c < ktot / 32; c += blockDim.x) {
+    float rmax = 0.f;
+    for (int i = c * 32; i < c * 32 + 32; ++i) {
+      const unsigned long long key = keys[i];
+      if (key != ~0ull) {
+        const float r = __uint_as_float((uint32_t)(key >> 32));
+        if (r <= rcap) rmax = fmaxf(rmax, r);
+      }
+    }
+    rmax *= slop;
+    ctab[2 * c] = 0.5f * (c1 + c2) * rmax;                      // A_c
+    ctab[2 * c + 1] = 0.5f * c2 * rmax * rmax + 1e-30f;         // B_c
+  }
+  for (int o = 16; o > 0; o >>= 1) rb = fminf(rb, __shfl_xor_sync(0xffffffffu, rb, o));
+  if ((tid & 31) == 0) red_min[tid >> 5] = rb;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) rb = fminf(rb, red_min[i]);
+    meta[0] = rcap;
+    meta[1] = rb / slop;
+  }
+  // sorted copy of the codebook rows (TMA source)
+  const int dq = D >> 2;
+  for (int i = tid; i < ktot * dq; i += blockDim.x) {
+    const int pos = i / dq, j = i - pos * dq;
+    const unsigned long long key = keys[pos];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (key != ~0ull) v = __ldg(reinterpret_cast<const float4*>(E + (size_t)(uint32_t)key * D) + j);
+    reinterpret_cast<float4*>(es + (size_t)pos * D)[j] = v;
   }
 }
 
@@ -250,10 +329,11 @@ vq_tc_prep2_kernel(const float* __restrict__ e2, int K, int D, int BN, int nb, f
 // ---------------------------------------------------------------------------------------------
 struct TcParams {
   const float* z; const float* E; const float* e2; const float* eaug_img; const float* meta;
+  const int* perm; const float* ctab;
   int B, D, H, W, HW, K;
   int BN, nb, nD, nst;
   int tiles_per_img; int ntiles;
-  uint32_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_bar;
+  uint32_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_ctab, off_bar;
   int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts; float* sums;
   int* fb_count; int* fb_rows;
   float* dbg;      // optional [N][nb*BN] dump of the raw accumulators
@@ -307,6 +387,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       a[i] = make_float4(v, v, v, v);
     }
     for (int k = t; k < P.K; k += 128) hist[k] = 0;
+    for (int c = t; c < 2 * P.nb * (P.BN >> 5); c += 128) ((float*)(smem + P.off_ctab))[c] = P.ctab[c];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -328,7 +409,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % P.nst, ph = (it / P.nst) & 1;
-        mbar_wait(BAR(3 + s), ph ^ 1);
+        mbar_wait_sleep(BAR(3 + s), ph ^ 1, 256);
         mbar_expect_tx(BAR(1 + s), zstage_bytes);
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
         for (int c = 0; c < P.nD; ++c)
@@ -345,12 +426,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % P.nst, ph = (it / P.nst) & 1;
-        mbar_wait(BAR(1 + s), ph);
+        mbar_wait_sleep(BAR(1 + s), ph, 32);
         tc_fence_after();
         const uint32_t zaddr = sbase + P.off_z + s * zstage_bytes;
         for (int blk = 0; blk < P.nb; ++blk, ++g) {
           const int a = g & 1, aph = (g >> 1) & 1;
-          mbar_wait(BAR(7 + a), aph ^ 1);
+          mbar_wait_sleep(BAR(7 + a), aph ^ 1, 32);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
           uint32_t acc = 0;
@@ -377,11 +458,20 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     // ===================================== epilogue =========================================
     const int quad = warp & 3;
     const int p = quad * 32 + lane;                       // pixel within the tile == TMEM lane
-    int* rec_c = (int*)(smem + P.off_rec);                // [TC_CL][128]
-    uint32_t* rec_m = (uint32_t*)(smem + P.off_rec + TC_CL * TC_TILE * 4);
-    const float R = P.meta[0], rminbig = P.meta[1], c1 = P.meta[2], c2 = P.meta[3];
+    const uint32_t rec_c = sbase + P.off_rec;             // [TC_CL][128] int: first column of the record's chunk
+    const uint32_t rec_m = rec_c + TC_CL * TC_TILE * 4;   // [TC_CL][128] u32: candidate mask of the chunk
+    const float rminbig = P.meta[1];
+    const uint32_t ctab_s = sbase + P.off_ctab;
     const int nchunks = P.BN >> 5;
     const int ncols = P.nb * P.BN;
+    const int nq = P.D >> 2;                              // channel quads
+    const uint32_t bn128 = (uint32_t)P.BN * 128;
+    // shared-memory address of z(p, d) = zrow + (d>>5)*16384 + (d&31)*128 + zx[d&3]   (see zs_off)
+    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
+    const uint32_t emain = sbase + P.off_emain;
     float lsum = 0.f;
     int g = 0;
     mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
@@ -389,16 +479,21 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = it % P.nst, ph = (it / P.nst) & 1;
       const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
-      const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
+      const uint32_t zrow = zrow0 + s * zstage_bytes;
       mbar_wait(BAR(1 + s), ph);
-      // |z|^2 (same fma chain as the CUDA-core kernel) and the row's error bound
+      // |z|^2 (same ascending-d fma chain as the CUDA-core kernel) and the row's error bound
       float z2 = 0.f;
-      for (int d = 0; d < P.D; ++d) {
-        const float v = *(const float*)(zs + zs_off(p, d));
-        z2 = __fmaf_rn(v, v, z2);
+      for (int j = 0; j < nq; ++j) {
+        const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+        const float v0 = lds_f32(zj + zx[0]), v1 = lds_f32(zj + zx[1]), v2 = lds_f32(zj + zx[2]), v3 = lds_f32(zj + zx[3]);
+        z2 = __fmaf_rn(v0, v0, z2);
+        z2 = __fmaf_rn(v1, v1, z2);
+        z2 = __fmaf_rn(v2, v2, z2);
+        z2 = __fmaf_rn(v3, v3, z2);
       }
       if (DBG) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
         float* o2 = P.dbg + (size_t)P.B * P.HW * ncols + ((size_t)b * P.HW + p0 + p) * 8;
+        const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
         const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
         o2[0] = z2;
         o2[1] = *(const float*)(zs + zs_off(p, 0));
@@ -411,8 +506,11 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       }
       const bool bad = !(z2 <= 3.0e38f);
       const float zn = sqrtf(z2) * 1.00001f;
-      const float bS = c1 * zn * R + c2 * R * (zn + R) + 1e-30f;   // |approx - exact| of S = 2*acc; acc threshold = bS
-      float M = -INFINITY;
+      // Running state of the scan (accumulator units, a_k = z.e_k - |e_k|^2/2):
+      //   L     lower bound on the best exact a_k seen so far   = max_c (chunkmax_c - delta_c)
+      //   Urec  upper bound on the exact a_k of every recorded candidate
+      // A column of chunk c is a candidate iff approx + delta_c >= L, i.e. approx >= L - delta_c.
+      float L = -INFINITY, Urec = -INFINITY;
       int cnt = 0;
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
@@ -422,6 +520,9 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         float v[32];
         for (int c = 0; c < nchunks; ++c) {
           tmem_ld32(taddr + c * 32, v);
+          float cA, cB;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)(blk * nchunks + c) * 8));
+          const float delta = __fmaf_rn(zn, cA, cB);
           tmem_ld_wait();
           if (DBG) {
             float* o = P.dbg + ((size_t)b * P.HW + p0 + p) * ncols + blk * P.BN + c * 32;
@@ -432,16 +533,20 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
           for (int j = 1; j < 31; j += 2) cm = fmaxf(fmaxf(cm, v[j]), v[j + 1]);
           cm = fmaxf(cm, v[31]);
-          if (cm - bS > M) cnt = 0;                       // everything recorded so far is out of range
-          M = fmaxf(M, cm);
-          const float T = M - bS;
+          L = fmaxf(L, cm - delta);
+          if (Urec < L) { cnt = 0; Urec = -INFINITY; }    // nothing recorded so far can still win
+          const float T = L - delta;
           uint32_t nm = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) nm = __funnelshift_l(__float_as_uint(v[j] - T), nm, 1);
           const uint32_t cand = ~nm;                      // bit (31-j) set <=> column j is within the bound
           if (cand) {
-            if (cnt < TC_CL) { rec_c[cnt * TC_TILE + p] = blk * P.BN + c * 32; rec_m[cnt * TC_TILE + p] = cand; }
+            if (cnt < TC_CL) {
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rec_c + (uint32_t)(cnt * TC_TILE + p) * 4), "r"(blk * P.BN + c * 32));
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rec_m + (uint32_t)(cnt * TC_TILE + p) * 4), "r"(cand));
+            }
             ++cnt;
+            Urec = fmaxf(Urec, cm + delta);
           }
         }
         tc_fence_before();
@@ -452,8 +557,18 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       // ---- exact stage ----------------------------------------------------------------------
       int total = 0;
       const int nrec = min(cnt, TC_CL);
-      for (int r = 0; r < nrec; ++r) total += __popc(rec_m[r * TC_TILE + p]);
-      const float lbest = 2.f * M - bS;
+      uint32_t rm[TC_CL];
+      int rc[TC_CL];
+#pragma unroll
+      for (int r = 0; r < TC_CL; ++r) {
+        rm[r] = 0; rc[r] = 0;
+        if (r < nrec) {
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rm[r]) : "r"(rec_m + (uint32_t)(r * TC_TILE + p) * 4));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rc[r]) : "r"(rec_c + (uint32_t)(r * TC_TILE + p) * 4));
+          total += __popc(rm[r]);
+        }
+      }
+      const float lbest = 2.f * L;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
       // excluded ("big") codes: s_k <= r_k (2|z| - r_k), decreasing in r_k for r_k >= |z|
       bool big_safe = true;
       if (rminbig < 3.0e38f) {
@@ -466,61 +581,66 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         const int slot = atomicAdd(P.fb_count, 1);
         P.fb_rows[slot] = (int)n;
       } else {
-        int w = -1;
-        if (total == 1) {
-          w = rec_c[p] + __clz(rec_m[p]);
-        } else {
+        int w = rc[0] + __clz(rm[0]);                     // position in the norm-sorted codebook
+        int worig = __ldg(P.perm + w);                    // original code index
+        if (total > 1) {
           float best = -INFINITY;
-          for (int r = 0; r < nrec; ++r) {
-            uint32_t m = rec_m[r * TC_TILE + p];
-            const int cbase = rec_c[r * TC_TILE + p];
+          w = -1;
+#pragma unroll
+          for (int r = 0; r < TC_CL; ++r) {
+            uint32_t m = rm[r];
             while (m) {
-              const int j = __clz(m);
-              m &= ~(0x80000000u >> j);
-              const int k = cbase + j;
+              const int jb = __clz(m);
+              m &= ~(0x80000000u >> jb);
+              const int k = rc[r] + jb;
               // exact fp32 score, reference op order (vq_module.py:54-57), ascending-d fma chain
-              const int blk = k / P.BN, row = k % P.BN;
-              const uint8_t* eb = smem + P.off_emain + (size_t)(blk * P.nD) * P.BN * 128 + row * 128;
+              const int kb = k / P.BN, row = k - kb * P.BN;
+              const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+              const uint32_t r7 = (uint32_t)(row & 7);
               float dot = 0.f;
-              for (int d = 0; d < P.D; d += 4) {
-                const float4 e4 = *(const float4*)(eb + (size_t)(d >> 5) * P.BN * 128 + ((((d & 31) >> 2) ^ (row & 7)) << 4));
-                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d)), e4.x, dot);
-                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 1)), e4.y, dot);
-                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 2)), e4.z, dot);
-                dot = __fmaf_rn(*(const float*)(zs + zs_off(p, d + 3)), e4.w, dot);
+              for (int j = 0; j < nq; ++j) {
+                const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
+                const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+                dot = __fmaf_rn(lds_f32(zj + zx[0]), e4.x, dot);
+                dot = __fmaf_rn(lds_f32(zj + zx[1]), e4.y, dot);
+                dot = __fmaf_rn(lds_f32(zj + zx[2]), e4.z, dot);
+                dot = __fmaf_rn(lds_f32(zj + zx[3]), e4.w, dot);
               }
-              const float sc = ref_score(dot, __ldg(P.e2 + k), z2);
-              if (sc > best || w < 0) { best = sc; w = k; }   // ascending k + strict '>' keeps the lowest index
+              const int korig = __ldg(P.perm + k);
+              const float sc = ref_score(dot, __ldg(P.e2 + korig), z2);
+              // ties go to the lowest ORIGINAL index, as in the CUDA-core kernel
+              if (w < 0 || sc > best || (sc == best && korig < worig)) { best = sc; w = k; worig = korig; }
             }
           }
         }
         // ---- outputs for the winner: ids, q, (z-q)^2, EMA statistics --------------------------
         const int pp = p0 + p;
-        const int h = pp / P.W, wc = pp % P.W;
-        if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = w;
-        if (P.ids_nat) P.ids_nat[n] = w;
-        if (P.counts) atomicAdd(&hist[w], 1);
-        const int blk = w / P.BN, row = w % P.BN;
-        const uint8_t* eb = smem + P.off_emain + (size_t)(blk * P.nD) * P.BN * 128 + row * 128;
+        const int h = pp / P.W, wc = pp - h * P.W;
+        if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = worig;
+        if (P.ids_nat) P.ids_nat[n] = worig;
+        if (P.counts) atomicAdd(&hist[worig], 1);
+        const int kb = w / P.BN, row = w - kb * P.BN;
+        const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+        const uint32_t r7 = (uint32_t)(row & 7);
         float* qo = P.q ? P.q + ((long long)b * P.D) * P.HW + pp : nullptr;
-        float* so = P.sums ? P.sums + (size_t)w * P.D : nullptr;
-        for (int d = 0; d < P.D; d += 4) {
-          const float4 e4 = *(const float4*)(eb + (size_t)(d >> 5) * P.BN * 128 + ((((d & 31) >> 2) ^ (row & 7)) << 4));
-          const float z0 = *(const float*)(zs + zs_off(p, d));
-          const float z1 = *(const float*)(zs + zs_off(p, d + 1));
-          const float z2v = *(const float*)(zs + zs_off(p, d + 2));
-          const float z3 = *(const float*)(zs + zs_off(p, d + 3));
+        float* so = P.sums ? P.sums + (size_t)worig * P.D : nullptr;
+        const size_t hw = (size_t)P.HW;
+        for (int j = 0; j < nq; ++j) {
+          const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
+          const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+          const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
           float df = z0 - e4.x; lsum = __fmaf_rn(df, df, lsum);
           df = z1 - e4.y; lsum = __fmaf_rn(df, df, lsum);
           df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
           df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
           if (qo) {
-            qo[(long long)d * P.HW] = e4.x;
-            qo[(long long)(d + 1) * P.HW] = e4.y;
-            qo[(long long)(d + 2) * P.HW] = e4.z;
-            qo[(long long)(d + 3) * P.HW] = e4.w;
+            __stcs(qo, e4.x);
+            __stcs(qo + hw, e4.y);
+            __stcs(qo + 2 * hw, e4.z);
+            __stcs(qo + 3 * hw, e4.w);
+            qo += 4 * hw;
           }
-          if (so) atomicAdd(reinterpret_cast<float4*>(so + d), make_float4(z0, z1, z2v, z3));
+          if (so) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
         }
       }
       __syncwarp();
@@ -578,7 +698,7 @@ static int sm_count_tc() {
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
   const TcGeom g = tc_geometry(a.D, a.K);
-  VQ_REQUIRE(g.ok && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
+  VQ_REQUIRE(g.ok && g.nb * g.BN <= TC_SORT_MAX && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
   EncodeTiledFn enc = get_encode_fn();
   VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
@@ -595,31 +715,34 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
   }
-  {   // codebook [K][D] row-major: dim0 = channel, dim1 = code; out-of-range rows / columns read as zero
-    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)a.K};
+  {   // norm-sorted codebook copy [nb*BN][D] row-major: dim0 = channel, dim1 = sorted code position
+    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)(g.nb * g.BN)};
     cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
     cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.embed, dims, strides, box, es,
+    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
   }
 
-  float* eaug_img = a.ws.tc_e;
+  float* eaug_img = a.ws.tc_aug;
   float* meta = a.ws.tc_meta;
-  vq_tc_prep2_kernel<<<1, 1024, 0, s>>>(a.ws.e2, a.K, a.D, g.BN, g.nb, eaug_img, meta);
+  vq_tc_prep2_kernel<<<1, 1024, 0, s>>>(a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm,
+                                        a.ws.tc_ctab, meta);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
 
   TcParams P{};
   P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
+  P.perm = a.ws.tc_perm; P.ctab = a.ws.tc_ctab;
   P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
   P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nst = g.nst;
   P.tiles_per_img = HW / TC_TILE;
   P.ntiles = a.B * P.tiles_per_img;
   P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;
   P.off_z = (uint32_t)g.off_z; P.off_rec = (uint32_t)g.off_rec; P.off_hist = (uint32_t)g.off_hist;
+  P.off_ctab = (uint32_t)g.off_ctab;
   P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
   P.counts = a.stats ? a.ws.counts : nullptr;

@@ -59,7 +59,7 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
     if (use_tc) {
       rc = launch_assign_tc(a, s);           // tcgen05 approximate search + exact fp32 re-rank
       if (rc) return rc;
-      rc = launch_assign_simt(a, /*fallback_list_mode=*/true, s);   // rows the bound could not decide
+      rc = launch_fallback_rows(a, s);       // exhaustive fp32 search of the rows the bound could not decide
       if (rc) return rc;
     } else {
       rc = launch_assign_simt(a, false, s);

@@ -53,15 +53,18 @@ struct Workspace {
   int* counts;       // [K]      exact int32 histogram
   int* misc;         // [8]      misc[0] = number of rows routed to the exact fallback search
   int* fb_rows;      // [N]      rows routed to the exact fallback search (tensor-core path)
-  float* tc_e;       // tensor-core operand: codebook + augmentation columns, see vq_assign_tc.cu
-  float* tc_meta;    // [16]     per-call scalars for the tensor-core path (bounds)
+  // tensor-core path (vq_assign_tc.cu): codebook sorted by norm, augmentation image, permutation, bounds
+  float* tc_es;      // [Kpad][D] codebook rows in ascending-norm order (zero rows for padding)
+  float* tc_aug;     // [Kpad*8]  shared-memory image of the augmentation columns (-|e|^2/2 split in tf32)
+  int* tc_perm;      // [Kpad]    sorted position -> original code index
+  float* tc_ctab;    // [Kpad/32][2] per 32-code chunk: error-bound coefficients (A, B)
+  float* tc_meta;    // [16]     per-call scalars (r_minbig, ...)
   size_t bytes;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline size_t stats_sums_offset(int K) { return align_up((size_t)2 * K, 4); }
 inline int pad_codes(int K) { return (int)align_up((size_t)K, kCodePad); }
-inline int tc_dpad(int D) { return (int)align_up((size_t)D + 8, 32); }   // D + 8 augmentation columns
 
 inline Workspace carve_workspace(void* base, int64_t N, int K, int D) {
   Workspace w;
@@ -75,7 +78,10 @@ inline Workspace carve_workspace(void* base, int64_t N, int K, int D) {
   w.counts = (int*)take(sizeof(int) * K);
   w.misc = (int*)take(sizeof(int) * 8);
   w.fb_rows = (int*)take(sizeof(int) * (size_t)(N > 0 ? N : 1));
-  w.tc_e = (float*)take(sizeof(float) * (size_t)Kpad * tc_dpad(D));
+  w.tc_es = (float*)take(sizeof(float) * (size_t)Kpad * D);
+  w.tc_aug = (float*)take(sizeof(float) * (size_t)Kpad * 8);
+  w.tc_perm = (int*)take(sizeof(int) * (size_t)Kpad);
+  w.tc_ctab = (float*)take(sizeof(float) * (size_t)(Kpad / 32) * 2);
   w.tc_meta = (float*)take(sizeof(float) * 16);
   w.bytes = off;
   return w;
@@ -97,6 +103,7 @@ int launch_assign_tc(const FwdArgs& a, cudaStream_t s);          // vq_assign_tc
 bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc.cu
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int tc_debug_ncols(int D, int K);
+int launch_fallback_rows(const FwdArgs& a, cudaStream_t s);
 int launch_finish(const FwdArgs& a, cudaStream_t s);
 int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,
                const float* stats, int K, int D, double momentum, double eps, float count_scale, float sum_scale,

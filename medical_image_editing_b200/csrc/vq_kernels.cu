@@ -315,6 +315,79 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
 }
 
 // =============================================================================================
+// exhaustive exact search for the few rows the tensor-core kernel could not decide: one warp per row,
+// codes spread over lanes (coalesced reads of the transposed codebook), same fma chains as above
+// =============================================================================================
+constexpr int FB_WARPS = 4;
+__global__ void __launch_bounds__(FB_WARPS * 32)
+vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ et, const float* __restrict__ e2,
+                        const float* __restrict__ E, int D, int H, int W, int K, int Kpad,
+                        const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
+                        int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat, float* __restrict__ q,
+                        double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums) {
+  extern __shared__ float zrow_all[];                 // [FB_WARPS][D]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* zr = zrow_all + (size_t)wib * D;
+  const int nrows = *fb_count;
+  const int HW = H * W;
+  const int gw = blockIdx.x * FB_WARPS + wib, nw = gridDim.x * FB_WARPS;
+  float lsum = 0.f;
+  for (int r = gw; r < nrows; r += nw) {
+    const long long n = fb_rows[r];
+    const long long b = n / HW, p = n - b * HW;
+    const long long off = b * (long long)D * HW + p;
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) zr[d] = __ldg(z + off + (long long)d * HW);
+    __syncwarp();
+    float z2 = 0.f;
+    for (int d = 0; d < D; ++d) z2 = __fmaf_rn(zr[d], zr[d], z2);
+    float best = -INFINITY;
+    int bi = 0;
+    for (int k0 = 0; k0 < Kpad; k0 += 256) {           // 8 codes per lane in flight: lane, lane+32, ..., lane+224
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      const float* ep = et + k0 + lane;
+#pragma unroll 2
+      for (int d = 0; d < D; ++d) {
+        const float zv = zr[d];
+        const float* row = ep + (size_t)d * Kpad;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(zv, __ldg(row + 32 * i), acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                    // ascending k per lane, strict '>' keeps the lowest index
+        const int k = k0 + lane + 32 * i;
+        const float sc = ref_score(acc[i], __ldg(e2 + k), z2);
+        if (sc > best) { best = sc; bi = k; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (!(best > -INFINITY)) bi = 0;                   // all-NaN row: the reference's topk returns index 0
+    if (lane == 0) {
+      const int h = (int)(p / W), w = (int)(p % W);
+      if (ids) ids[b * HW + (long long)w * H + h] = bi;
+      if (ids_nat) ids_nat[n] = bi;
+      if (counts) atomicAdd(&counts[bi], 1);
+    }
+    for (int d = lane; d < D; d += 32) {
+      const float ev = __ldg(E + (size_t)bi * D + d);
+      const float df = zr[d] - ev;
+      lsum = __fmaf_rn(df, df, lsum);
+      if (q) q[off + (long long)d * HW] = ev;
+      if (sums) atomicAdd(sums + (size_t)bi * D + d, zr[d]);
+    }
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0 && loss_acc && lsum != 0.f) atomicAdd(loss_acc, (double)lsum);
+}
+
+// =============================================================================================
 // finish: loss = acc / (N*D); pack the int32 histogram as two exactly-representable floats
 // =============================================================================================
 __global__ void vq_finish_kernel(const double* __restrict__ loss_acc, float* __restrict__ loss, double inv_numel,
@@ -574,6 +647,18 @@ int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s
                                                a.ids, a.ids_nat, a.q, a.ws.loss_acc,
                                                a.stats ? a.ws.counts : nullptr, sums);
   if (prof) profile_end(s);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
+int launch_fallback_rows(const FwdArgs& a, cudaStream_t s) {
+  const int Kpad = pad_codes(a.K);
+  float* sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
+  const size_t smem = (size_t)FB_WARPS * a.D * sizeof(float);
+  vq_fallback_rows_kernel<<<2 * sm_count(), FB_WARPS * 32, smem, s>>>(
+      a.z, a.ws.et, a.ws.e2, a.embed, a.D, a.H, a.W, a.K, Kpad, a.ws.fb_rows, a.ws.misc, a.ids, a.ids_nat, a.q,
+      a.ws.loss_acc, a.stats ? a.ws.counts : nullptr, sums);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;

@@ -35,7 +35,10 @@ if ncols:
           "tmem_base bits:", dbg2[0, 7].view(torch.int32).item())
     flat = z.permute(0, 2, 3, 1).reshape(N, D).double()
     ref = flat @ E.double().T - 0.5 * E.double().pow(2).sum(1)[None]
-    got = out[:, :K].double()
+    # columns are in ascending-norm order of the codes: undo the permutation
+    order = torch.argsort(E.pow(2).sum(1).sqrt(), stable=True)
+    got = torch.empty_like(ref)
+    got[:, order] = out[:, :K].double()
     err = (got - ref).abs()
     print("nan count", int(torch.isnan(out[:, :K]).sum()), "max abs err", float(err.nan_to_num(1e9).max()),
           "mean abs err", float(err.nan_to_num(0).mean()))
@@ -68,3 +71,23 @@ print("ids equal", torch.equal(outs[0][0], outs[1][0]), "mismatch", int((outs[0]
 print("q equal", torch.equal(outs[0][1], outs[1][1]))
 print("loss", outs[0][2], outs[1][2])
 print("cluster_size equal", torch.equal(outs[0][3], outs[1][3]), "embed maxdiff", float((outs[0][4] - outs[1][4]).abs().max()))
+
+# several training steps: fallback rows and time per step as the codebook evolves
+from medical_image_editing_b200.src.functions import vq_function as vf
+m = pkg.VQ(emb_dim=D, dict_size=K, momentum=0.99, eps=1e-5, knn_backend="torch").to(dev)
+with torch.no_grad():
+    m.embed.copy_(E); m.embed_avg.copy_(E.T)
+m.train(True)
+for step in range(6):
+    zz = torch.randn(B, D, H, H, device=dev, generator=g)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    norms = m.embed.norm(dim=1)
+    e0.record()
+    with torch.no_grad():
+        q, loss, ids = m(zz)
+    e1.record()
+    torch.cuda.synchronize()
+    wsb = list(vf._WORKSPACES.values())[0]
+    fbr = L.vq_debug_fallback_rows(wsb.data_ptr(), N, K, D, torch.cuda.current_stream().cuda_stream)
+    print(f"step {step}: fwd {e0.elapsed_time(e1):.3f} ms, fallback rows {fbr}, code norms min/med/max "
+          f"{norms.min().item():.3g}/{norms.median().item():.3g}/{norms.max().item():.3g}, loss {loss.item():.4f}")
