@@ -1,21 +1,26 @@
 // vq_assign_tc.cu -- tcgen05 / TMEM / TMA nearest-code search with exact fp32 re-rank (sm_100a).
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: codebook once (resident in shared memory), then one 128-pixel z tile per
-//               stage, loaded straight from NCHW (pixel-contiguous => MN-major A operand, no flatten copy)
-//   warp 1      MMA issuer: tcgen05.mma kind::tf32, M=128 pixels x N<=256 codes x K=8 per instruction,
-//               fp32 accumulators in TMEM (2 stages x 256 columns); one extra K-step multiplies a block of
-//               ones with a 3-way tf32 split of -|e|^2/2, so the accumulator holds z.e - |e|^2/2 directly
-//   warps 2..5  epilogue, thread = pixel: tcgen05.ld 32 columns at a time, running max (FMNMX3) and a
-//               sign-bit candidate mask against (max - bound) (FADD + SHF); then EXACT fp32 scores of the
-//               surviving candidates in the reference's op order, gather of q, (z-q)^2, EMA statistics.
+// One persistent CTA per SM (640 threads), warp-specialised:
+//   warp 0       TMA producer: codebook once (resident in shared memory), then one 128-pixel z tile per
+//                stage, loaded straight from NCHW (pixel-contiguous => MN-major A operand, no flatten copy)
+//   warp 1       MMA issuer: tcgen05.mma kind::tf32, M=128 pixels x N<=256 codes x K=8 per instruction,
+//                fp32 accumulators in TMEM (2 stages x 256 columns); one extra K-step multiplies a block of
+//                ones with a 3-way tf32 split of -|e|^2/2, so the accumulator holds z.e - |e|^2/2 directly
+//   warps 2,3    |z|^2 of the tile's pixels (bound of the tf32 error, last term of the exact score)
+//   warps 4..19  epilogue, warp = (TMEM lane quadrant, column group): thread = (pixel, quarter of the codes).
+//                scan: tcgen05.ld 32 columns at a time, running max (FMNMX3) and a sign-bit candidate mask
+//                against (max - bound) (FADD + SHF); the four column groups of a pixel merge their bounds
+//                through shared memory; pixels left with >1 candidate put (pixel, code) pairs on a per-quadrant
+//                work list that the quadrant's warps score in EXACT fp32 (reference op order), lanes over
+//                channels; then every thread gathers q, (z-q)^2 and the EMA statistics for a quarter of the
+//                channels of its pixel.
 //
 // Exactness: tf32 drops 13 mantissa bits of z and e, so an approximate score can be off by at most
 //   b = 2^-8 |z| |e|  (+ accumulation slop).  Every code whose approximate score is within 2b of the
-//   approximate maximum is re-scored in exact fp32 (same fma chain as the CUDA-core kernel), so the
-//   winner is the fp32 winner.  Rows with more candidates than the kernel keeps, non-finite rows, or rows
-//   where a norm-outlier ("exploded") code could still win are appended to a list that the CUDA-core
-//   kernel then searches exhaustively.  Nothing is probabilistic.
+//   approximate maximum is re-scored in exact fp32, so the winner is the fp32 winner.  Rows with more
+//   candidates than the kernel keeps, non-finite rows, or rows where a norm-outlier ("exploded") code could
+//   still win are appended to a list that a CUDA-core kernel then searches exhaustively.  Nothing is
+//   probabilistic.
 #include <cuda.h>
 #include <math.h>
 
@@ -29,15 +34,19 @@ namespace vqb200 {
 constexpr int TC_TILE = 128;        // pixels per tile (UMMA M)
 constexpr int TC_MAXBN = 256;       // codes per accumulator stage (UMMA N)
 constexpr int TC_DCH = 32;          // channels per shared-memory chunk (128-byte swizzle rows)
-constexpr int TC_THREADS = 192;     // producer warp, MMA warp, 4 epilogue warps
-constexpr int TC_CL = 4;            // candidate records per pixel
-constexpr int TC_CMAX = 8;          // candidates re-scored per pixel before falling back
+constexpr int TC_NCG = 4;           // column groups: epilogue warps per TMEM lane quadrant
+constexpr int TC_EPI_WARPS = 4 * TC_NCG;
+constexpr int TC_AUX_WARPS = 4;     // TMA producer, MMA issuer, two |z|^2 workers
+constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_EPI_WARPS);
+constexpr int TC_WLCAP = 64;        // (pixel, code) pairs re-scored exactly per quadrant and tile
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SORT_MAX = 4096;     // codes the single-CTA sort of vq_tc_prep2_kernel handles
+constexpr int TC_MAX_REP = 32;        // replicas of the per-code sums (spreads the L2 reduction traffic)
 
 struct TcGeom {
   int BN, nb, nD, nst;
-  size_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_ctab, off_bar, total;
+  size_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_best, off_wl, off_zn, off_hist, off_perm,
+      off_ctab, off_bar, total;
   bool ok;
 };
 
@@ -47,27 +56,44 @@ static TcGeom tc_geometry(int D, int K) {
   g.BN = K > 128 ? 256 : (int)align_up((size_t)K, 32);
   g.nb = (K + g.BN - 1) / g.BN;
   g.nD = (D + TC_DCH - 1) / TC_DCH;
-  const size_t emain = (size_t)g.nb * g.nD * g.BN * 128;
-  const size_t eaug = (size_t)g.nb * g.BN * 32;
+  const size_t ktot = (size_t)g.nb * g.BN;
+  const size_t emain = ktot * g.nD * 128;
+  const size_t eaug = ktot * 32;
   const size_t zstage = (size_t)g.nD * TC_TILE * 128;
   size_t off = 0;
   g.off_emain = off; off += emain;
   g.off_eaug = off;  off += align_up(eaug, 1024);
   g.off_aaug = off;  off += 4096;
   g.off_z = off;
-  const size_t ctab_bytes = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
-  const size_t tail = (size_t)2 * TC_CL * TC_TILE * 4 + align_up((size_t)K * 4, 16) + ctab_bytes + 256;
+  const size_t sz_pub = (size_t)TC_NCG * TC_TILE * 8, sz_win = TC_TILE * 4, sz_best = 2 * TC_TILE * 8;
+  const size_t sz_wl = 4 * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 8;
+  const size_t sz_hist = align_up((size_t)K * 4, 16), sz_perm = align_up(ktot * 2, 16);
+  const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
+  const size_t tail = sz_pub + sz_win + sz_best + sz_wl + sz_zn + sz_hist + sz_perm + sz_ctab + 256;
   for (int nst = 2; nst >= 1; --nst) {
     if (off + nst * zstage + tail + 1024 <= (size_t)TC_SMEM_LIMIT) { g.nst = nst; g.ok = true; break; }
   }
   if (!g.ok) return g;
   off += g.nst * zstage;
-  g.off_rec = off;  off += (size_t)2 * TC_CL * TC_TILE * 4;
-  g.off_hist = off; off += align_up((size_t)K * 4, 16);
-  g.off_ctab = off; off += ctab_bytes;
+  g.off_pub = off;  off += sz_pub;
+  g.off_win = off;  off += sz_win;
+  g.off_best = off; off += sz_best;
+  g.off_wl = off;   off += sz_wl;
+  g.off_zn = off;   off += sz_zn;
+  g.off_hist = off; off += sz_hist;
+  g.off_perm = off; off += sz_perm;
+  g.off_ctab = off; off += sz_ctab;
   g.off_bar = off;  off += 256;
   g.total = off + 1024;   // slack for manual 1024-byte alignment of the dynamic smem base
   return g;
+}
+
+int tc_sums_replicas(int K, int D) {
+  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 4 MB in total
+  size_t r = ((size_t)4 << 20) / ((size_t)K * D * 4);
+  if (r > (size_t)TC_MAX_REP) r = TC_MAX_REP;
+  if (r < 1) r = 1;
+  return (int)r;
 }
 
 bool tc_path_supported(int B, int D, int H, int W, int K) {
@@ -333,8 +359,12 @@ struct TcParams {
   int B, D, H, W, HW, K;
   int BN, nb, nD, nst;
   int tiles_per_img; int ntiles;
-  uint32_t off_emain, off_eaug, off_aaug, off_z, off_rec, off_hist, off_ctab, off_bar;
-  int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts; float* sums;
+  uint32_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_best, off_wl, off_zn, off_hist, off_perm,
+      off_ctab, off_bar;
+  int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
+  float* sums;            // replica 0 of the per-code sums (inside the packed statistics buffer), or null
+  float* sums_rep;        // replicas 1..nrep-1 (workspace), [nrep-1][K*D]
+  int nrep;
   int* fb_count; int* fb_rows;
   float* dbg;      // optional [N][nb*BN] dump of the raw accumulators
 };
@@ -348,6 +378,22 @@ __device__ __forceinline__ uint32_t zs_off(int p, int d) {
                     ((((p & 31) >> 2) ^ ((row & 3) << 1)) << 4) + ((p & 3) << 2));
 }
 
+__device__ __forceinline__ void quad_bar(int quad) {      // the NCG warps that share one TMEM lane quadrant
+  asm volatile("bar.sync %0, %1;" ::"r"(quad + 1), "n"(32 * TC_NCG) : "memory");
+}
+__device__ __forceinline__ uint32_t f32_orderable(float x) {   // monotone map float -> uint32
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// round a float UP to a value whose low 16 bits are zero (conservative 16-bit copy of an upper bound)
+__device__ __forceinline__ uint32_t f32_up16(float x) {
+  const uint32_t u = __float_as_uint(x);
+  if (u & 0x80000000u) return u & 0xFFFF0000u;              // negative: shrinking the magnitude moves up
+  return (u + 0xFFFFu) & 0xFFFF0000u;                        // positive: bump the magnitude (inf stays inf)
+}
+
+constexpr unsigned long long TC_KEY_FALLBACK = ~0ull;
+
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
@@ -358,36 +404,48 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 
   uint64_t* bars = (uint64_t*)(smem + P.off_bar);
   const uint32_t bar0 = sbase + P.off_bar;
-  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty ; slot 9: tmem base
+  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty | 9,10 zn_full
+  // slot 11: tmem base ; slots 12,13: work-list counters of the four quadrants (4 x int)
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+  int* wl_count = (int*)(bars + 12);
   int* hist = (int*)(smem + P.off_hist);
+  unsigned long long* best = (unsigned long long*)(smem + P.off_best);
+  int* win = (int*)(smem + P.off_win);
+  uint16_t* perm_s = (uint16_t*)(smem + P.off_perm);
+  float2* znb = (float2*)(smem + P.off_zn);                 // [nst][128]: (bound on |z|, |z|^2)
 
   const uint32_t zstage_bytes = (uint32_t)P.nD * TC_TILE * 128;
+  const int ktot = P.nb * P.BN;
 
   if (threadIdx.x == 32) {
     mbar_init(BAR(0), 1);
     mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-    mbar_init(BAR(3), 4); mbar_init(BAR(4), 4);
+    mbar_init(BAR(3), TC_EPI_WARPS + 2); mbar_init(BAR(4), TC_EPI_WARPS + 2);
     mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-    mbar_init(BAR(7), 4); mbar_init(BAR(8), 4);
+    mbar_init(BAR(7), TC_EPI_WARPS); mbar_init(BAR(8), TC_EPI_WARPS);
+    mbar_init(BAR(9), 2); mbar_init(BAR(10), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
+  if (warp >= TC_AUX_WARPS) {
     // ones block of the augmentation K-step: 4 groups x 8 rows x 128 B; rows 0..2 = 1, rows 3..7 = 0
-    const int t = threadIdx.x - 64;                       // 0..127
+    const int t = threadIdx.x - 32 * TC_AUX_WARPS;        // 0 .. 32*TC_EPI_WARPS-1
+    constexpr int NT = 32 * TC_EPI_WARPS;
     float4* a = (float4*)(smem + P.off_aaug);
-    for (int i = t; i < 256; i += 128) {                  // 256 float4 = 4 KB
+    for (int i = t; i < 256; i += NT) {                   // 256 float4 = 4 KB
       const int row = (i >> 3) & 7;
       const float v = row < 3 ? 1.f : 0.f;
       a[i] = make_float4(v, v, v, v);
     }
-    for (int k = t; k < P.K; k += 128) hist[k] = 0;
-    for (int c = t; c < 2 * P.nb * (P.BN >> 5); c += 128) ((float*)(smem + P.off_ctab))[c] = P.ctab[c];
+    for (int k = t; k < P.K; k += NT) hist[k] = 0;
+    for (int k = t; k < ktot; k += NT) perm_s[k] = (uint16_t)P.perm[k];
+    for (int c = t; c < 2 * P.nb * (P.BN >> 5); c += NT) ((float*)(smem + P.off_ctab))[c] = P.ctab[c];
+    if (t < 4) wl_count[t] = 0;
+    for (int i = t; i < 2 * TC_TILE; i += NT) best[i] = 0ull;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -409,7 +467,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % P.nst, ph = (it / P.nst) & 1;
-        mbar_wait_sleep(BAR(3 + s), ph ^ 1, 256);
+        mbar_wait_sleep(BAR(3 + s), ph ^ 1, 128);
         mbar_expect_tx(BAR(1 + s), zstage_bytes);
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
         for (int c = 0; c < P.nD; ++c)
@@ -454,16 +512,44 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
       }
     }
+  } else if (warp < TC_AUX_WARPS) {
+    // ===================================== |z|^2 workers ====================================
+    // two warps, two pixels per lane; same ascending-d fma chain as the CUDA-core kernels
+    const int pA = (warp - 2) * 64 + lane;                // second pixel: pA + 32 (same swizzle phase)
+    const int nq = P.D >> 2;
+    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((pA & 31) >> 2) ^ (i << 1)) << 4);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % P.nst, ph = (it / P.nst) & 1;
+      mbar_wait(BAR(1 + s), ph);
+      const uint32_t zrow = zrow0 + s * zstage_bytes;
+      float za = 0.f, zb = 0.f;
+      for (int j = 0; j < nq; ++j) {
+        const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float va = lds_f32(zj + zx[i]), vb = lds_f32(zj + 4096 + zx[i]);
+          za = __fmaf_rn(va, va, za);
+          zb = __fmaf_rn(vb, vb, zb);
+        }
+      }
+      znb[s * TC_TILE + pA] = make_float2(sqrtf(za) * 1.00001f, za);
+      znb[s * TC_TILE + pA + 32] = make_float2(sqrtf(zb) * 1.00001f, zb);
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(BAR(9 + s)); mbar_arrive(BAR(3 + s)); }
+    }
   } else {
     // ===================================== epilogue =========================================
-    const int quad = warp & 3;
+    // warp = (quad, cg): TMEM lane quadrant `quad` (pixels quad*32 .. +31), column group cg: scans the 32-code
+    // chunks c == cg (mod TC_NCG) of every block, then handles the channel quads j == cg (mod TC_NCG) of its pixel.
+    const int quad = warp & 3, cg = (warp - TC_AUX_WARPS) >> 2;
     const int p = quad * 32 + lane;                       // pixel within the tile == TMEM lane
-    const uint32_t rec_c = sbase + P.off_rec;             // [TC_CL][128] int: first column of the record's chunk
-    const uint32_t rec_m = rec_c + TC_CL * TC_TILE * 4;   // [TC_CL][128] u32: candidate mask of the chunk
     const float rminbig = P.meta[1];
     const uint32_t ctab_s = sbase + P.off_ctab;
     const int nchunks = P.BN >> 5;
-    const int ncols = P.nb * P.BN;
+    const int ncols = ktot;
     const int nq = P.D >> 2;                              // channel quads
     const uint32_t bn128 = (uint32_t)P.BN * 128;
     // shared-memory address of z(p, d) = zrow + (d>>5)*16384 + (d&31)*128 + zx[d&3]   (see zs_off)
@@ -472,6 +558,13 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t emain = sbase + P.off_emain;
+    const uint32_t pub_s = sbase + P.off_pub;             // [TC_NCG][128] uint2
+    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)quad * (TC_WLCAP * 4);   // this quadrant's work list
+    float* sums_mine = nullptr;
+    if (P.sums) {
+      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
+      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * P.D;
+    }
     float lsum = 0.f;
     int g = 0;
     mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
@@ -480,18 +573,13 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const int s = it % P.nst, ph = (it / P.nst) & 1;
       const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
       const uint32_t zrow = zrow0 + s * zstage_bytes;
+      mbar_wait(BAR(9 + s), ph);                          // |z|^2 ready (implies the z tile landed)
       mbar_wait(BAR(1 + s), ph);
-      // |z|^2 (same ascending-d fma chain as the CUDA-core kernel) and the row's error bound
-      float z2 = 0.f;
-      for (int j = 0; j < nq; ++j) {
-        const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-        const float v0 = lds_f32(zj + zx[0]), v1 = lds_f32(zj + zx[1]), v2 = lds_f32(zj + zx[2]), v3 = lds_f32(zj + zx[3]);
-        z2 = __fmaf_rn(v0, v0, z2);
-        z2 = __fmaf_rn(v1, v1, z2);
-        z2 = __fmaf_rn(v2, v2, z2);
-        z2 = __fmaf_rn(v3, v3, z2);
-      }
-      if (DBG) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
+      const float2 zz = znb[s * TC_TILE + p];
+      const float zn = zz.x, z2 = zz.y;
+      const bool bad = !(z2 <= 3.0e38f);
+      unsigned long long* bestc = best + (it & 1) * TC_TILE;     // this tile's slots; the other half is reset below
+      if (DBG && cg == 0) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
         float* o2 = P.dbg + (size_t)P.B * P.HW * ncols + ((size_t)b * P.HW + p0 + p) * 8;
         const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
         const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
@@ -504,21 +592,21 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         o2[6] = *(const float*)(smem + P.off_aaug + p * 4);
         o2[7] = __uint_as_float(tmem_base);
       }
-      const bool bad = !(z2 <= 3.0e38f);
-      const float zn = sqrtf(z2) * 1.00001f;
-      // Running state of the scan (accumulator units, a_k = z.e_k - |e_k|^2/2):
-      //   L     lower bound on the best exact a_k seen so far   = max_c (chunkmax_c - delta_c)
+      // ---- scan: this warp's chunks of every block -------------------------------------------
+      // Running state (accumulator units, a_k = z.e_k - |e_k|^2/2):
+      //   L     lower bound on the best exact a_k among the columns this thread has seen = max_c (chunkmax_c - delta_c)
       //   Urec  upper bound on the exact a_k of every recorded candidate
       // A column of chunk c is a candidate iff approx + delta_c >= L, i.e. approx >= L - delta_c.
       float L = -INFINITY, Urec = -INFINITY;
-      int cnt = 0;
+      int cnt = 0, rc0 = 0, rc1 = 0;
+      uint32_t rm0 = 0, rm1 = 0;
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
         mbar_wait(BAR(5 + a), aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
-        float v[32];
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = cg; c < nchunks; c += TC_NCG) {
+          float v[32];
           tmem_ld32(taddr + c * 32, v);
           float cA, cB;
           asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)(blk * nchunks + c) * 8));
@@ -529,22 +617,32 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = v[j];
           }
-          float cm = v[0];
+          float m4[4];
 #pragma unroll
-          for (int j = 1; j < 31; j += 2) cm = fmaxf(fmaxf(cm, v[j]), v[j + 1]);
-          cm = fmaxf(cm, v[31]);
+          for (int h = 0; h < 4; ++h) {                   // four independent max chains (8 columns each)
+            float m = fmaxf(fmaxf(v[8 * h], v[8 * h + 1]), v[8 * h + 2]);
+            m = fmaxf(fmaxf(m, v[8 * h + 3]), v[8 * h + 4]);
+            m = fmaxf(fmaxf(m, v[8 * h + 5]), v[8 * h + 6]);
+            m4[h] = fmaxf(m, v[8 * h + 7]);
+          }
+          const float cm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           L = fmaxf(L, cm - delta);
           if (Urec < L) { cnt = 0; Urec = -INFINITY; }    // nothing recorded so far can still win
           const float T = L - delta;
-          uint32_t nm = 0;
+          uint32_t n4[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) nm = __funnelshift_l(__float_as_uint(v[j] - T), nm, 1);
-          const uint32_t cand = ~nm;                      // bit (31-j) set <=> column j is within the bound
+          for (int h = 0; h < 4; ++h) {                   // four independent sign-bit chains
+            uint32_t nm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nm = __funnelshift_l(__float_as_uint(v[8 * h + j] - T), nm, 1);
+            n4[h] = nm;
+          }
+          const uint32_t nmall = (n4[0] << 24) | (n4[1] << 16) | (n4[2] << 8) | n4[3];
+          const uint32_t cand = ~nmall;                   // bit (31-j) set <=> column j is within the bound
           if (cand) {
-            if (cnt < TC_CL) {
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rec_c + (uint32_t)(cnt * TC_TILE + p) * 4), "r"(blk * P.BN + c * 32));
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rec_m + (uint32_t)(cnt * TC_TILE + p) * 4), "r"(cand));
-            }
+            const int col = blk * P.BN + c * 32;
+            if (cnt == 0) { rc0 = col; rm0 = cand; }
+            else if (cnt == 1) { rc1 = col; rm1 = cand; }
             ++cnt;
             Urec = fmaxf(Urec, cm + delta);
           }
@@ -554,78 +652,140 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         if (lane == 0) mbar_arrive(BAR(7 + a));
       }
 
-      // ---- exact stage ----------------------------------------------------------------------
-      int total = 0;
-      const int nrec = min(cnt, TC_CL);
-      uint32_t rm[TC_CL];
-      int rc[TC_CL];
-#pragma unroll
-      for (int r = 0; r < TC_CL; ++r) {
-        rm[r] = 0; rc[r] = 0;
-        if (r < nrec) {
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rm[r]) : "r"(rec_m + (uint32_t)(r * TC_TILE + p) * 4));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rc[r]) : "r"(rec_c + (uint32_t)(r * TC_TILE + p) * 4));
-          total += __popc(rm[r]);
-        }
+      // ---- merge the column groups of each pixel ------------------------------------------------
+      if (cnt < 2) rm1 = 0;
+      if (cnt < 1) rm0 = 0;
+      const uint32_t nC = (uint32_t)(__popc(rm0) + __popc(rm1));
+      {
+        const uint32_t w1 = f32_up16(Urec) | (cnt > 2 ? 0x100u : 0u) | nC;   // nC <= 64
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_s + (uint32_t)(cg * TC_TILE + p) * 8),
+                     "r"(__float_as_uint(L)), "r"(w1) : "memory");
       }
-      const float lbest = 2.f * L;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
+      quad_bar(quad);                                     // (A) everybody's (L, U, count) is published
+      if (cg == 0) best[((it + 1) & 1) * TC_TILE + p] = 0ull;   // next tile's slot: its last readers passed (A)
+      uint32_t pw[TC_NCG];
+      float Lg = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < TC_NCG; ++i) {
+        uint32_t l;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(pw[i]) : "r"(pub_s + (uint32_t)(i * TC_TILE + p) * 8));
+        Lg = fmaxf(Lg, __uint_as_float(l));
+      }
+      int total = 0;
+      bool ovf = false, alive = false;
+#pragma unroll
+      for (int i = 0; i < TC_NCG; ++i) {
+        const bool al = __uint_as_float(pw[i] & 0xFFFF0000u) >= Lg;
+        if (al) { total += (int)(pw[i] & 0xFFu); ovf |= (pw[i] & 0x100u) != 0; }
+        if (i == cg) alive = al;
+      }
+      const float lbest = 2.f * Lg;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
       // excluded ("big") codes: s_k <= r_k (2|z| - r_k), decreasing in r_k for r_k >= |z|
       bool big_safe = true;
       if (rminbig < 3.0e38f) {
         const float bigub = rminbig * (2.f * zn - rminbig);
         big_safe = (rminbig >= zn) && (bigub + 1e-5f * (fabsf(bigub) + fabsf(lbest)) < lbest);
       }
-      const bool fb = bad || cnt > TC_CL || total == 0 || total > TC_CMAX || !big_safe;
-      const long long n = (long long)b * P.HW + p0 + p;
-      if (fb) {
-        const int slot = atomicAdd(P.fb_count, 1);
-        P.fb_rows[slot] = (int)n;
-      } else {
-        int w = rc[0] + __clz(rm[0]);                     // position in the norm-sorted codebook
-        int worig = __ldg(P.perm + w);                    // original code index
-        if (total > 1) {
-          float best = -INFINITY;
-          w = -1;
-#pragma unroll
-          for (int r = 0; r < TC_CL; ++r) {
-            uint32_t m = rm[r];
+      bool fb = bad || ovf || total == 0 || !big_safe;
+      if (!fb && alive) {
+        if (total == 1) {
+          win[p] = rc0 + __clz(rm0);                      // nC == 1 => the single candidate sits in record 0
+        } else {
+          const int slot = atomicAdd(&wl_count[quad], (int)nC);
+          if (slot + (int)nC <= TC_WLCAP) {
+            uint32_t wa = wl_s + (uint32_t)slot * 4;
+            uint32_t m = rm0;
             while (m) {
               const int jb = __clz(m);
               m &= ~(0x80000000u >> jb);
-              const int k = rc[r] + jb;
-              // exact fp32 score, reference op order (vq_module.py:54-57), ascending-d fma chain
-              const int kb = k / P.BN, row = k - kb * P.BN;
-              const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
-              const uint32_t r7 = (uint32_t)(row & 7);
-              float dot = 0.f;
-              for (int j = 0; j < nq; ++j) {
-                const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
-                const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-                dot = __fmaf_rn(lds_f32(zj + zx[0]), e4.x, dot);
-                dot = __fmaf_rn(lds_f32(zj + zx[1]), e4.y, dot);
-                dot = __fmaf_rn(lds_f32(zj + zx[2]), e4.z, dot);
-                dot = __fmaf_rn(lds_f32(zj + zx[3]), e4.w, dot);
-              }
-              const int korig = __ldg(P.perm + k);
-              const float sc = ref_score(dot, __ldg(P.e2 + korig), z2);
-              // ties go to the lowest ORIGINAL index, as in the CUDA-core kernel
-              if (w < 0 || sc > best || (sc == best && korig < worig)) { best = sc; w = k; worig = korig; }
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(((uint32_t)p << 16) | (uint32_t)(rc0 + jb)) : "memory");
+              wa += 4;
             }
+            m = rm1;
+            while (m) {
+              const int jb = __clz(m);
+              m &= ~(0x80000000u >> jb);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(((uint32_t)p << 16) | (uint32_t)(rc1 + jb)) : "memory");
+              wa += 4;
+            }
+          } else {
+            atomicMax(&bestc[p], TC_KEY_FALLBACK);         // work list full: exhaustive search for this pixel
           }
         }
-        // ---- outputs for the winner: ids, q, (z-q)^2, EMA statistics --------------------------
+      }
+      quad_bar(quad);                                     // (C) winners of single-candidate pixels and the work list are visible
+      const int nitems = min(wl_count[quad], TC_WLCAP);
+      if (nitems > 0) {
+        // ---- exact fp32 re-rank of the listed (pixel, code) pairs: one warp per pair, lanes over channel quads ----
+        for (int i = cg; i < nitems; i += TC_NCG) {
+          uint32_t item;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
+          const int pp = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+          const int kb = k / P.BN, row = k - kb * P.BN;
+          const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+          const uint32_t r7 = (uint32_t)(row & 7);
+          const uint32_t zr = sbase + P.off_z + s * zstage_bytes + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
+          const uint32_t xs = (uint32_t)((pp & 31) >> 2);
+          float dot = 0.f;
+          for (int j = lane; j < nq; j += 32) {
+            const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
+            const uint32_t zj = zr + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+            dot = __fmaf_rn(lds_f32(zj + ((xs ^ 0u) << 4)), e4.x, dot);
+            dot = __fmaf_rn(lds_f32(zj + 128 + ((xs ^ 2u) << 4)), e4.y, dot);
+            dot = __fmaf_rn(lds_f32(zj + 256 + ((xs ^ 4u) << 4)), e4.z, dot);
+            dot = __fmaf_rn(lds_f32(zj + 384 + ((xs ^ 6u) << 4)), e4.w, dot);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          if (lane == 0) {
+            const int korig = perm_s[k];
+            // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
+            const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(kb * P.BN * 32 + (row >> 3) * 256 + (row & 7) * 16));
+            const float e2k = -2.f * ((au.z + au.y) + au.x);
+            const float sc = ref_score(dot, e2k, znb[s * TC_TILE + pp].y);
+            // ties go to the lowest ORIGINAL index
+            const unsigned long long key = ((unsigned long long)f32_orderable(sc) << 32) |
+                                           ((unsigned long long)(0xFFFFu - (uint32_t)korig) << 16) | (unsigned long long)k;
+            atomicMax(&bestc[pp], key);
+          }
+        }
+        quad_bar(quad);                                   // (D) all pairs of this quadrant are scored
+        if (cg == 0 && lane == 0) wl_count[quad] = 0;
+      }
+      int w = 0;
+      if (!fb) {
+        if (total == 1) {
+          w = win[p];
+        } else {
+          const unsigned long long key = bestc[p];
+          if (key == TC_KEY_FALLBACK || key == 0ull) fb = true;
+          else w = (int)(key & 0xFFFFull);
+        }
+      }
+
+      // ---- outputs: ids, q, (z-q)^2, EMA statistics (channel quads j == cg mod TC_NCG) ------------
+      const long long n = (long long)b * P.HW + p0 + p;
+      if (fb) {
+        if (cg == 0) {
+          const int slot = atomicAdd(P.fb_count, 1);
+          P.fb_rows[slot] = (int)n;
+        }
+      } else {
+        const int worig = perm_s[w];
         const int pp = p0 + p;
-        const int h = pp / P.W, wc = pp - h * P.W;
-        if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = worig;
-        if (P.ids_nat) P.ids_nat[n] = worig;
-        if (P.counts) atomicAdd(&hist[worig], 1);
+        if (cg == 0) {
+          const int h = pp / P.W, wc = pp - h * P.W;
+          if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = worig;
+          if (P.ids_nat) P.ids_nat[n] = worig;
+          if (P.counts) atomicAdd(&hist[worig], 1);
+        }
         const int kb = w / P.BN, row = w - kb * P.BN;
         const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
         const uint32_t r7 = (uint32_t)(row & 7);
-        float* qo = P.q ? P.q + ((long long)b * P.D) * P.HW + pp : nullptr;
-        float* so = P.sums ? P.sums + (size_t)worig * P.D : nullptr;
         const size_t hw = (size_t)P.HW;
-        for (int j = 0; j < nq; ++j) {
+        float* qo = P.q ? P.q + ((long long)b * P.D) * P.HW + pp : nullptr;
+        float* so = sums_mine ? sums_mine + (size_t)worig * P.D : nullptr;
+        for (int j = cg; j < nq; j += TC_NCG) {
           const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
           const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
           const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
@@ -634,11 +794,11 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
           df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
           if (qo) {
-            __stcs(qo, e4.x);
-            __stcs(qo + hw, e4.y);
-            __stcs(qo + 2 * hw, e4.z);
-            __stcs(qo + 3 * hw, e4.w);
-            qo += 4 * hw;
+            float* qj = qo + (size_t)(4 * j) * hw;
+            __stcs(qj, e4.x);
+            __stcs(qj + hw, e4.y);
+            __stcs(qj + 2 * hw, e4.z);
+            __stcs(qj + 3 * hw, e4.w);
           }
           if (so) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
         }
@@ -648,10 +808,10 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     }
     // ---- per-CTA reductions ------------------------------------------------------------------
     lsum = warp_sum(lsum);
-    if (lane == 0 && P.loss_acc) atomicAdd(P.loss_acc, (double)lsum);
-    asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+    if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
+    asm volatile("bar.sync 5, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");        // all epilogue warps
     if (P.counts) {
-      for (int k = threadIdx.x - 64; k < P.K; k += 128) {
+      for (int k = threadIdx.x - 32 * TC_AUX_WARPS; k < P.K; k += 32 * TC_EPI_WARPS) {
         const int c = hist[k];
         if (c) atomicAdd(&P.counts[k], c);
       }
@@ -741,12 +901,15 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   P.tiles_per_img = HW / TC_TILE;
   P.ntiles = a.B * P.tiles_per_img;
   P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;
-  P.off_z = (uint32_t)g.off_z; P.off_rec = (uint32_t)g.off_rec; P.off_hist = (uint32_t)g.off_hist;
-  P.off_ctab = (uint32_t)g.off_ctab;
+  P.off_z = (uint32_t)g.off_z; P.off_pub = (uint32_t)g.off_pub; P.off_win = (uint32_t)g.off_win;
+  P.off_best = (uint32_t)g.off_best; P.off_wl = (uint32_t)g.off_wl; P.off_zn = (uint32_t)g.off_zn;
+  P.off_hist = (uint32_t)g.off_hist; P.off_perm = (uint32_t)g.off_perm; P.off_ctab = (uint32_t)g.off_ctab;
   P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
   P.counts = a.stats ? a.ws.counts : nullptr;
   P.sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
+  P.sums_rep = a.ws.sums_rep;
+  P.nrep = tc_sums_replicas(a.K, a.D);
   P.fb_count = a.ws.misc; P.fb_rows = a.ws.fb_rows;
   P.dbg = dbg;
 

@@ -66,7 +66,7 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
       if (rc) return rc;
     }
   }
-  return launch_finish(a, s);
+  return launch_finish(a, use_tc, s);
 }
 
 int vq_ema_update(float* cluster_size, float* embed_avg, int64_t avg_stride_d, int64_t avg_stride_k, float* embed,

@@ -59,12 +59,15 @@ struct Workspace {
   int* tc_perm;      // [Kpad]    sorted position -> original code index
   float* tc_ctab;    // [Kpad/32][2] per 32-code chunk: error-bound coefficients (A, B)
   float* tc_meta;    // [16]     per-call scalars (r_minbig, ...)
+  float* sums_rep;   // [R-1][K*D] extra replicas of the per-code sums (R = tc_sums_replicas(K, D)); summed by finish
   size_t bytes;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline size_t stats_sums_offset(int K) { return align_up((size_t)2 * K, 4); }
 inline int pad_codes(int K) { return (int)align_up((size_t)K, kCodePad); }
+
+int tc_sums_replicas(int K, int D);                              // vq_assign_tc.cu
 
 inline Workspace carve_workspace(void* base, int64_t N, int K, int D) {
   Workspace w;
@@ -83,6 +86,7 @@ inline Workspace carve_workspace(void* base, int64_t N, int K, int D) {
   w.tc_perm = (int*)take(sizeof(int) * (size_t)Kpad);
   w.tc_ctab = (float*)take(sizeof(float) * (size_t)(Kpad / 32) * 2);
   w.tc_meta = (float*)take(sizeof(float) * 16);
+  w.sums_rep = (float*)take(sizeof(float) * (size_t)(tc_sums_replicas(K, D) - 1) * K * D + 16);
   w.bytes = off;
   return w;
 }
@@ -104,7 +108,7 @@ bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int tc_debug_ncols(int D, int K);
 int launch_fallback_rows(const FwdArgs& a, cudaStream_t s);
-int launch_finish(const FwdArgs& a, cudaStream_t s);
+int launch_finish(const FwdArgs& a, bool tc_path, cudaStream_t s);
 int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,
                const float* stats, int K, int D, double momentum, double eps, float count_scale, float sum_scale,
                float* scratch, cudaStream_t s);

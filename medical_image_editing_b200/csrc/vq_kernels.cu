@@ -87,8 +87,8 @@ int profile_read(double* total_ms, int* launches) {
 // =============================================================================================
 __global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kpad,
                                float* __restrict__ e2, float* __restrict__ et, float* __restrict__ snap,
-                               float* __restrict__ stats, size_t stats_n, int* __restrict__ counts,
-                               double* __restrict__ loss_acc, int* __restrict__ misc) {
+                               float* __restrict__ stats, size_t stats_n, float* __restrict__ sums_rep, size_t rep_n,
+                               int* __restrict__ counts, double* __restrict__ loss_acc, int* __restrict__ misc) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nth = (size_t)gridDim.x * blockDim.x;
   // |e_k|^2 : one thread per code, ascending d, fused multiply-add chain
@@ -114,6 +114,7 @@ __global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kp
   }
   if (stats) {
     for (size_t i = tid; i < stats_n; i += nth) stats[i] = 0.f;
+    for (size_t i = tid; i < rep_n; i += nth) sums_rep[i] = 0.f;
   }
   for (size_t i = tid; i < (size_t)K; i += nth) counts[i] = 0;
   if (tid == 0) *loss_acc = 0.0;
@@ -391,7 +392,8 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
 // finish: loss = acc / (N*D); pack the int32 histogram as two exactly-representable floats
 // =============================================================================================
 __global__ void vq_finish_kernel(const double* __restrict__ loss_acc, float* __restrict__ loss, double inv_numel,
-                                 const int* __restrict__ counts, float* __restrict__ stats, int K) {
+                                 const int* __restrict__ counts, float* __restrict__ stats, int K, int D,
+                                 size_t sums_off, const float* __restrict__ sums_rep, int nrep) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0 && loss) *loss = (float)(*loss_acc * inv_numel);
   if (stats) {
@@ -399,6 +401,14 @@ __global__ void vq_finish_kernel(const double* __restrict__ loss_acc, float* __r
       const int c = counts[k];
       stats[k] = (float)(c >> 12);
       stats[K + k] = (float)(c & 4095);
+    }
+    if (nrep > 1) {                       // fold the replicas of the per-code sums (fixed order)
+      const int kd = K * D;
+      for (int i = tid; i < kd; i += gridDim.x * blockDim.x) {
+        float acc = stats[sums_off + i];
+        for (int r = 0; r < nrep - 1; ++r) acc += sums_rep[(size_t)r * kd + i];
+        stats[sums_off + i] = acc;
+      }
     }
   }
 }
@@ -615,15 +625,17 @@ static int sm_count() {
   return n;
 }
 
-int launch_prep(const FwdArgs& a, bool /*tc_path*/, cudaStream_t s) {
+int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s) {
   const int Kpad = pad_codes(a.K);
   const size_t work = (size_t)a.D * Kpad;
   int blocks = (int)((work + 255) / 256);
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   if (blocks < 1) blocks = 1;
   const size_t stats_n = a.stats ? vq_stats_floats(a.K, a.D) : 0;
+  const size_t rep_n = (a.stats && tc_path) ? (size_t)(tc_sums_replicas(a.K, a.D) - 1) * a.K * a.D : 0;
+  if (rep_n > 0 && blocks < 2 * sm_count()) blocks = 2 * sm_count();
   vq_prep_kernel<<<blocks, 256, 0, s>>>(a.embed, a.K, a.D, Kpad, a.ws.e2, a.ws.et, a.snapshot, a.stats, stats_n,
-                                        a.ws.counts, a.ws.loss_acc, a.ws.misc);
+                                        a.ws.sums_rep, rep_n, a.ws.counts, a.ws.loss_acc, a.ws.misc);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;
@@ -664,10 +676,17 @@ int launch_fallback_rows(const FwdArgs& a, cudaStream_t s) {
   return VQ_OK;
 }
 
-int launch_finish(const FwdArgs& a, cudaStream_t s) {
+int launch_finish(const FwdArgs& a, bool tc_path, cudaStream_t s) {
   const double numel = (double)a.B * a.D * a.H * a.W;
-  const int blocks = a.stats ? (a.K + 255) / 256 : 1;
-  vq_finish_kernel<<<blocks, 256, 0, s>>>(a.ws.loss_acc, a.loss, 1.0 / numel, a.ws.counts, a.stats, a.K);
+  const int nrep = (a.stats && tc_path) ? tc_sums_replicas(a.K, a.D) : 1;
+  int blocks = 1;
+  if (a.stats) {
+    const long long work = nrep > 1 ? (long long)a.K * a.D : (long long)a.K;
+    blocks = (int)((work + 255) / 256);
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  }
+  vq_finish_kernel<<<blocks, 256, 0, s>>>(a.ws.loss_acc, a.loss, 1.0 / numel, a.ws.counts, a.stats, a.K, a.D,
+                                          stats_sums_offset(a.K), a.ws.sums_rep, nrep);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;
