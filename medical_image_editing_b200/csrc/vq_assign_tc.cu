@@ -53,7 +53,8 @@ struct TcGeom {
 static TcGeom tc_geometry(int D, int K) {
   TcGeom g{};
   g.ok = false;
-  g.BN = K > 128 ? 256 : (int)align_up((size_t)K, 32);
+  g.BN = 32;                                   // power of two (the epilogue shifts by it), <= 256
+  while (g.BN < K && g.BN < TC_MAXBN) g.BN <<= 1;
   g.nb = (K + g.BN - 1) / g.BN;
   g.nD = (D + TC_DCH - 1) / TC_DCH;
   const size_t ktot = (size_t)g.nb * g.BN;
@@ -358,6 +359,8 @@ struct TcParams {
   const int* perm; const float* ctab;
   int B, D, H, W, HW, K;
   int BN, nb, nD, nst;
+  int bn_shift;           // BN == 1 << bn_shift
+  int w_shift;            // W == 1 << w_shift, or -1
   int tiles_per_img; int ntiles;
   uint32_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_best, off_wl, off_zn, off_hist, off_perm,
       off_ctab, off_bar;
@@ -411,7 +414,6 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   int* wl_count = (int*)(bars + 12);
   int* hist = (int*)(smem + P.off_hist);
   unsigned long long* best = (unsigned long long*)(smem + P.off_best);
-  int* win = (int*)(smem + P.off_win);
   uint16_t* perm_s = (uint16_t*)(smem + P.off_perm);
   float2* znb = (float2*)(smem + P.off_zn);                 // [nst][128]: (bound on |z|, |z|^2)
 
@@ -550,7 +552,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     const uint32_t ctab_s = sbase + P.off_ctab;
     const int nchunks = P.BN >> 5;
     const int ncols = ktot;
-    const int nq = P.D >> 2;                              // channel quads
+    const int bnsh = P.bn_shift;                          // BN == 1 << bnsh
     const uint32_t bn128 = (uint32_t)P.BN * 128;
     // shared-memory address of z(p, d) = zrow + (d>>5)*16384 + (d&31)*128 + zx[d&3]   (see zs_off)
     const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
@@ -558,30 +560,39 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t emain = sbase + P.off_emain;
-    const uint32_t pub_s = sbase + P.off_pub;             // [TC_NCG][128] uint2
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 8;                  // [TC_NCG][128] uint2, this pixel's column
     const uint32_t wl_s = sbase + P.off_wl + (uint32_t)quad * (TC_WLCAP * 4);   // this quadrant's work list
+    const uint32_t zn_s = sbase + P.off_zn;
+    const uint32_t best_s = sbase + P.off_best;
+    const uint32_t win_s = sbase + P.off_win + (uint32_t)p * 4;
+    const uint32_t perm_a = sbase + P.off_perm;
     float* sums_mine = nullptr;
     if (P.sums) {
       const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
-      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * P.D;
+      sums_mine = (rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * P.D) + 4 * cg;
     }
+    const size_t hw = (size_t)P.HW;
+    const size_t img_stride = (size_t)P.D * hw;
     float lsum = 0.f;
     int g = 0;
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile -> (image, tile in image)
     mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int s = it % P.nst, ph = (it / P.nst) & 1;
-      const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
-      const uint32_t zrow = zrow0 + s * zstage_bytes;
+      const int s = P.nst == 2 ? (it & 1) : 0, ph = P.nst == 2 ? ((it >> 1) & 1) : (it & 1);
+      const int b = tb, p0 = tpt * TC_TILE;
+      tpt += (int)gridDim.x;
+      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
+      const uint32_t zst = s * zstage_bytes;
+      const uint32_t zrow = zrow0 + zst;
       mbar_wait(BAR(9 + s), ph);                          // |z|^2 ready (implies the z tile landed)
       mbar_wait(BAR(1 + s), ph);
-      const float2 zz = znb[s * TC_TILE + p];
-      const float zn = zz.x, z2 = zz.y;
+      float zn, z2;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(zn), "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 8));
       const bool bad = !(z2 <= 3.0e38f);
-      unsigned long long* bestc = best + (it & 1) * TC_TILE;     // this tile's slots; the other half is reset below
+      const uint32_t bestc = best_s + (uint32_t)(it & 1) * (TC_TILE * 8);   // this tile's slots; the other half is reset below
       if (DBG && cg == 0) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
         float* o2 = P.dbg + (size_t)P.B * P.HW * ncols + ((size_t)b * P.HW + p0 + p) * 8;
-        const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
+        const uint8_t* zs = smem + P.off_z + zst;
         const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
         o2[0] = z2;
         o2[1] = *(const float*)(zs + zs_off(p, 0));
@@ -598,7 +609,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       //   Urec  upper bound on the exact a_k of every recorded candidate
       // A column of chunk c is a candidate iff approx + delta_c >= L, i.e. approx >= L - delta_c.
       float L = -INFINITY, Urec = -INFINITY;
-      int cnt = 0, rc0 = 0, rc1 = 0;
+      int cnt = 0, rc0 = 0, rc1 = 0;                      // records: first column of the chunk, candidate mask
       uint32_t rm0 = 0, rm1 = 0;
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
@@ -639,13 +650,14 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           }
           const uint32_t nmall = (n4[0] << 24) | (n4[1] << 16) | (n4[2] << 8) | n4[3];
           const uint32_t cand = ~nmall;                   // bit (31-j) set <=> column j is within the bound
-          if (cand) {
-            const int col = blk * P.BN + c * 32;
-            if (cnt == 0) { rc0 = col; rm0 = cand; }
-            else if (cnt == 1) { rc1 = col; rm1 = cand; }
-            ++cnt;
-            Urec = fmaxf(Urec, cm + delta);
-          }
+          // branch-free record update
+          const bool has = cand != 0u;
+          const bool s0 = has && cnt == 0, s1 = has && cnt == 1;
+          const int col = (blk << bnsh) + c * 32;
+          rc0 = s0 ? col : rc0; rm0 = s0 ? cand : rm0;
+          rc1 = s1 ? col : rc1; rm1 = s1 ? cand : rm1;
+          cnt += has ? 1 : 0;
+          Urec = has ? fmaxf(Urec, cm + delta) : Urec;
         }
         tc_fence_before();
         __syncwarp();
@@ -658,17 +670,18 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const uint32_t nC = (uint32_t)(__popc(rm0) + __popc(rm1));
       {
         const uint32_t w1 = f32_up16(Urec) | (cnt > 2 ? 0x100u : 0u) | nC;   // nC <= 64
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_s + (uint32_t)(cg * TC_TILE + p) * 8),
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_s + (uint32_t)cg * (TC_TILE * 8)),
                      "r"(__float_as_uint(L)), "r"(w1) : "memory");
       }
       quad_bar(quad);                                     // (A) everybody's (L, U, count) is published
-      if (cg == 0) best[((it + 1) & 1) * TC_TILE + p] = 0ull;   // next tile's slot: its last readers passed (A)
+      if (cg == 0)                                        // next tile's slot: its last readers passed (A)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(best_s + (uint32_t)((it + 1) & 1) * (TC_TILE * 8) + (uint32_t)p * 8), "r"(0u) : "memory");
       uint32_t pw[TC_NCG];
       float Lg = -INFINITY;
 #pragma unroll
       for (int i = 0; i < TC_NCG; ++i) {
         uint32_t l;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(pw[i]) : "r"(pub_s + (uint32_t)(i * TC_TILE + p) * 8));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(pw[i]) : "r"(pub_s + (uint32_t)i * (TC_TILE * 8)));
         Lg = fmaxf(Lg, __uint_as_float(l));
       }
       int total = 0;
@@ -676,7 +689,8 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
       for (int i = 0; i < TC_NCG; ++i) {
         const bool al = __uint_as_float(pw[i] & 0xFFFF0000u) >= Lg;
-        if (al) { total += (int)(pw[i] & 0xFFu); ovf |= (pw[i] & 0x100u) != 0; }
+        total += al ? (int)(pw[i] & 0xFFu) : 0;
+        ovf |= al && (pw[i] & 0x100u) != 0;
         if (i == cg) alive = al;
       }
       const float lbest = 2.f * Lg;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
@@ -689,64 +703,69 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       bool fb = bad || ovf || total == 0 || !big_safe;
       if (!fb && alive) {
         if (total == 1) {
-          win[p] = rc0 + __clz(rm0);                      // nC == 1 => the single candidate sits in record 0
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s), "r"(rc0 + __clz(rm0)) : "memory");   // nC == 1 => record 0
         } else {
           const int slot = atomicAdd(&wl_count[quad], (int)nC);
-          if (slot + (int)nC <= TC_WLCAP) {
-            uint32_t wa = wl_s + (uint32_t)slot * 4;
-            uint32_t m = rm0;
-            while (m) {
+          // pairs that do not fit send the pixel to the exhaustive search; the slots below the capacity are
+          // still filled so that every listed pair is valid
+          if (slot + (int)nC > TC_WLCAP)
+            atomicMax((unsigned long long*)(smem + P.off_best) + (it & 1) * TC_TILE + p, TC_KEY_FALLBACK);
+          uint32_t wa = wl_s + (uint32_t)slot * 4;
+          const uint32_t wend = wl_s + TC_WLCAP * 4;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            uint32_t m = r ? rm1 : rm0;
+            const uint32_t base = ((uint32_t)p << 16) | (uint32_t)(r ? rc1 : rc0);
+            while (m && wa < wend) {
               const int jb = __clz(m);
               m &= ~(0x80000000u >> jb);
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(((uint32_t)p << 16) | (uint32_t)(rc0 + jb)) : "memory");
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
               wa += 4;
             }
-            m = rm1;
-            while (m) {
-              const int jb = __clz(m);
-              m &= ~(0x80000000u >> jb);
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(((uint32_t)p << 16) | (uint32_t)(rc1 + jb)) : "memory");
-              wa += 4;
-            }
-          } else {
-            atomicMax(&bestc[p], TC_KEY_FALLBACK);         // work list full: exhaustive search for this pixel
           }
         }
       }
       quad_bar(quad);                                     // (C) winners of single-candidate pixels and the work list are visible
       const int nitems = min(wl_count[quad], TC_WLCAP);
       if (nitems > 0) {
-        // ---- exact fp32 re-rank of the listed (pixel, code) pairs: one warp per pair, lanes over channel quads ----
-        for (int i = cg; i < nitems; i += TC_NCG) {
-          uint32_t item;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
-          const int pp = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-          const int kb = k / P.BN, row = k - kb * P.BN;
-          const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
-          const uint32_t r7 = (uint32_t)(row & 7);
-          const uint32_t zr = sbase + P.off_z + s * zstage_bytes + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
-          const uint32_t xs = (uint32_t)((pp & 31) >> 2);
-          float dot = 0.f;
-          for (int j = lane; j < nq; j += 32) {
-            const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
-            const uint32_t zj = zr + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-            dot = __fmaf_rn(lds_f32(zj + ((xs ^ 0u) << 4)), e4.x, dot);
-            dot = __fmaf_rn(lds_f32(zj + 128 + ((xs ^ 2u) << 4)), e4.y, dot);
-            dot = __fmaf_rn(lds_f32(zj + 256 + ((xs ^ 4u) << 4)), e4.z, dot);
-            dot = __fmaf_rn(lds_f32(zj + 384 + ((xs ^ 6u) << 4)), e4.w, dot);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-          if (lane == 0) {
-            const int korig = perm_s[k];
+        // ---- exact fp32 re-rank of the listed (pixel, code) pairs ----------------------------------
+        // One warp of the quadrant (rotating), one lane per pair: the dot product is the same ascending-d fma
+        // chain as in the CUDA-core kernels (which reproduces the reference's fp32 GEMM for these sizes).
+        if (cg == (it & (TC_NCG - 1))) {
+          const int nq = P.D >> 2;
+          for (int i = lane; i < nitems; i += 32) {
+            uint32_t item;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
+            const int pp = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+            const int kb = k >> bnsh, row = k & (P.BN - 1);
+            uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+            const uint32_t r7 = (uint32_t)(row & 7);
+            uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
+            const uint32_t xs = (uint32_t)((pp & 31) >> 2);
+            const uint32_t x0 = xs << 4, x1 = 128 + ((xs ^ 2u) << 4), x2 = 256 + ((xs ^ 4u) << 4), x3 = 384 + ((xs ^ 6u) << 4);
+            float dot = 0.f;
+            for (int j0 = 0; j0 < nq; j0 += 8) {            // one 32-channel chunk per iteration
+              const int jn = min(8, nq - j0);
+              for (int jj = 0; jj < jn; ++jj) {
+                const float4 e4 = lds_v4(eb + ((((uint32_t)jj) ^ r7) << 4));
+                const uint32_t zj = zr + (uint32_t)jj * 512;
+                dot = __fmaf_rn(lds_f32(zj + x0), e4.x, dot);
+                dot = __fmaf_rn(lds_f32(zj + x1), e4.y, dot);
+                dot = __fmaf_rn(lds_f32(zj + x2), e4.z, dot);
+                dot = __fmaf_rn(lds_f32(zj + x3), e4.w, dot);
+              }
+              eb += bn128; zr += 16384;
+            }
+            uint32_t korig;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
             // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
-            const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(kb * P.BN * 32 + (row >> 3) * 256 + (row & 7) * 16));
+            const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
             const float e2k = -2.f * ((au.z + au.y) + au.x);
-            const float sc = ref_score(dot, e2k, znb[s * TC_TILE + pp].y);
+            const float sc = ref_score(dot, e2k, lds_f32(zn_s + (uint32_t)(s * TC_TILE + pp) * 8 + 4));
             // ties go to the lowest ORIGINAL index
             const unsigned long long key = ((unsigned long long)f32_orderable(sc) << 32) |
-                                           ((unsigned long long)(0xFFFFu - (uint32_t)korig) << 16) | (unsigned long long)k;
-            atomicMax(&bestc[pp], key);
+                                           ((unsigned long long)(0xFFFFu - korig) << 16) | (unsigned long long)k;
+            atomicMax((unsigned long long*)(smem + P.off_best) + (it & 1) * TC_TILE + pp, key);
           }
         }
         quad_bar(quad);                                   // (D) all pairs of this quadrant are scored
@@ -755,52 +774,67 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       int w = 0;
       if (!fb) {
         if (total == 1) {
-          w = win[p];
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(win_s));
         } else {
-          const unsigned long long key = bestc[p];
-          if (key == TC_KEY_FALLBACK || key == 0ull) fb = true;
-          else w = (int)(key & 0xFFFFull);
+          uint32_t klo, khi;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(klo), "=r"(khi) : "r"(bestc + (uint32_t)p * 8));
+          if ((klo & khi) == 0xFFFFFFFFu || (klo | khi) == 0u) fb = true;
+          else w = (int)(klo & 0xFFFFu);
         }
       }
 
       // ---- outputs: ids, q, (z-q)^2, EMA statistics (channel quads j == cg mod TC_NCG) ------------
-      const long long n = (long long)b * P.HW + p0 + p;
+      const int pp = p0 + p;
       if (fb) {
         if (cg == 0) {
           const int slot = atomicAdd(P.fb_count, 1);
-          P.fb_rows[slot] = (int)n;
+          P.fb_rows[slot] = b * P.HW + pp;
         }
       } else {
-        const int worig = perm_s[w];
-        const int pp = p0 + p;
+        uint32_t worig;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(worig) : "r"(perm_a + (uint32_t)w * 2));
         if (cg == 0) {
-          const int h = pp / P.W, wc = pp - h * P.W;
-          if (P.ids) P.ids[(long long)b * P.HW + (long long)wc * P.H + h] = worig;
-          if (P.ids_nat) P.ids_nat[n] = worig;
+          int h, wc;
+          if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
+          else { h = pp / P.W; wc = pp - h * P.W; }
+          const size_t nb_ = (size_t)b * hw;
+          if (P.ids) P.ids[nb_ + (size_t)(wc * P.H + h)] = (int64_t)worig;
+          if (P.ids_nat) P.ids_nat[nb_ + pp] = (int)worig;
           if (P.counts) atomicAdd(&hist[worig], 1);
         }
-        const int kb = w / P.BN, row = w - kb * P.BN;
-        const uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+        const int kb = w >> bnsh, row = w & (P.BN - 1);
         const uint32_t r7 = (uint32_t)(row & 7);
-        const size_t hw = (size_t)P.HW;
-        float* qo = P.q ? P.q + ((long long)b * P.D) * P.HW + pp : nullptr;
+        // two quads per 32-channel chunk for this thread: jj = cg and cg + 4
+        uint32_t ea = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
+        uint32_t za = zrow + (uint32_t)cg * 512;
+        const uint32_t eo0 = (((uint32_t)cg ^ r7) << 4), eo1 = ((((uint32_t)cg + 4) ^ r7) << 4);
+        float* qo = P.q ? P.q + (size_t)b * img_stride + (size_t)(4 * cg) * hw + pp : nullptr;
         float* so = sums_mine ? sums_mine + (size_t)worig * P.D : nullptr;
-        for (int j = cg; j < nq; j += TC_NCG) {
-          const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
-          const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-          const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
-          float df = z0 - e4.x; lsum = __fmaf_rn(df, df, lsum);
-          df = z1 - e4.y; lsum = __fmaf_rn(df, df, lsum);
-          df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
-          df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
-          if (qo) {
-            float* qj = qo + (size_t)(4 * j) * hw;
-            __stcs(qj, e4.x);
-            __stcs(qj + hw, e4.y);
-            __stcs(qj + 2 * hw, e4.z);
-            __stcs(qj + 3 * hw, e4.w);
+        int d0 = 4 * cg;                                  // first channel of this thread's quad in the current chunk
+        for (int ci = 0; ci < P.nD; ++ci) {
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            if (d0 + 16 * hq < P.D) {
+              const float4 e4 = lds_v4(ea + (hq ? eo1 : eo0));
+              const uint32_t zj = za + (uint32_t)hq * 2048;
+              const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
+              float df = z0 - e4.x; lsum = __fmaf_rn(df, df, lsum);
+              df = z1 - e4.y; lsum = __fmaf_rn(df, df, lsum);
+              df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
+              df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
+              if (qo) {
+                float* qj = qo + (size_t)(16 * hq) * hw;
+                __stcs(qj, e4.x);
+                __stcs(qj + hw, e4.y);
+                __stcs(qj + 2 * hw, e4.z);
+                __stcs(qj + 3 * hw, e4.w);
+              }
+              if (so) atomicAdd(reinterpret_cast<float4*>(so + 16 * hq), make_float4(z0, z1, z2v, z3));
+            }
           }
-          if (so) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
+          ea += bn128; za += 16384; d0 += 32;
+          if (qo) qo += 32 * hw;
+          if (so) so += 32;
         }
       }
       __syncwarp();
@@ -898,6 +932,10 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   P.perm = a.ws.tc_perm; P.ctab = a.ws.tc_ctab;
   P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
   P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nst = g.nst;
+  P.bn_shift = 0;
+  while ((1 << P.bn_shift) < g.BN) ++P.bn_shift;
+  P.w_shift = -1;
+  if ((a.W & (a.W - 1)) == 0) { P.w_shift = 0; while ((1 << P.w_shift) < a.W) ++P.w_shift; }
   P.tiles_per_img = HW / TC_TILE;
   P.ntiles = a.B * P.tiles_per_img;
   P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;

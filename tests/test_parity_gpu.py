@@ -387,6 +387,38 @@ def test_simt_and_auto_paths_agree_at_full_size():
     assert rel_err(outs[1][4], outs[0][4]) <= TOL
 
 
+def test_multistep_cold_training_paths_agree():
+    """Several training steps from the cold state (cluster_size == 0): dead codes explode, many pixels
+    collapse onto a few live codes, candidate lists overflow -- the tensor-core path (with its exhaustive
+    fallback) must keep choosing exactly what the fp32 CUDA-core search chooses."""
+    B, D, H, K = 4, 64, 256, 512
+    gen = torch.Generator(device=DEV).manual_seed(2024)
+    embed = torch.randn(K, D, device=DEV, generator=gen)
+    ms = []
+    for flags in (_native.VQ_FLAG_FORCE_SIMT, 0):
+        m = new_vq(K, D, 0.99, flags)
+        with torch.no_grad():
+            m.embed.copy_(embed)
+            m.embed_avg.copy_(embed.T)
+        m.train(True)
+        ms.append(m)
+    assert _native.lib().vq_assign_path(B, D, H, H, K, 0) == 1
+    for step in range(5):
+        z = torch.randn(B, D, H, H, device=DEV, generator=gen)
+        if step == 3:
+            z = torch.relu(z)                       # post-ReLU statistics: many exact zeros
+        with torch.no_grad():
+            outs = [m(z) for m in ms]
+        assert torch.equal(outs[0][2], outs[1][2]), f"step {step}: ids differ"
+        assert torch.equal(outs[0][0], outs[1][0]), f"step {step}: quantized differs"
+        assert abs(outs[0][1].item() - outs[1][1].item()) <= TOL * abs(outs[0][1].item())
+        assert torch.equal(ms[0].cluster_size, ms[1].cluster_size)
+        assert rel_err(ms[1].embed, ms[0].embed) <= TOL
+        with torch.no_grad():                       # keep the two replicas bit-identical for the next step
+            for a, b in zip(ms[1].buffers(), ms[0].buffers()):
+                a.copy_(b)
+
+
 def test_embed_avg_layouts():
     """`embed.T.clone()` (vq_module.py:156) keeps strides (1, D); a checkpoint round trip can make the
     buffer contiguous.  Both must give the reference's update."""
