@@ -144,6 +144,9 @@ int vq_debug_tc_ncols(int D, int K);
 int vq_debug_tc_scores(const float* z, int B, int D, int H, int W, const float* embed, int K, float* out,
                        void* workspace, size_t workspace_bytes, vq_stream_t stream);
 int vq_debug_fallback_rows(const void* workspace, int64_t N, int K, int D, vq_stream_t stream);
+/* Phase timing of the tensor-core epilogue (only in builds with -DVQ_TC_TIMING; returns 0 otherwise): HOST buffer of
+ * 148*16*16 int64 clock sums [cta][epilogue warp][phase]. */
+int vq_debug_tc_timing(long long* host_out, int n);
 int vq_profile_enable(int on);
 int vq_profile_read(double* total_ms, int* launches);
 

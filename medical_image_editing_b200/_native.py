@@ -47,6 +47,7 @@ SIGNATURES = {
                                           ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "vq_debug_fallback_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p]),
+    "vq_debug_tc_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "vq_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "vq_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
 }

@@ -14,7 +14,7 @@ OBJS=""
 PIDS=""
 for s in $SRCS; do
   o="${s%.cu}.o"
-  $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$s" -o "$o" &
+  $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} ${VQ_EXTRA_FLAGS:-} -c "$s" -o "$o" &
   PIDS="$PIDS $!"
   OBJS="$OBJS $o"
 done

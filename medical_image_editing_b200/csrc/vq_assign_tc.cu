@@ -397,7 +397,23 @@ __device__ __forceinline__ uint32_t f32_up16(float x) {
 
 constexpr unsigned long long TC_KEY_FALLBACK = ~0ull;
 
-template <bool DBG>
+// Optional phase timing of the epilogue (build with -DVQ_TC_TIMING; read with vq_debug_tc_timing): clock64 deltas
+// summed over tiles by lane 0 of every epilogue warp.  Phases: 0 wait z | 1 scan | 2 merge (A) | 3 push (C) |
+// 4 re-rank (D) | 5 outputs | 6 tiles
+#ifdef VQ_TC_TIMING
+__device__ long long g_tc_timing[148 * TC_EPI_WARPS * 16];
+#define TC_TICK(slot)                                                   \
+  do {                                                                  \
+    const long long _now = clock64();                                   \
+    tacc[slot] += _now - tlast;                                         \
+    tlast = _now;                                                       \
+  } while (0)
+#else
+#define TC_TICK(slot) do { } while (0)
+#endif
+
+// DT: compile-time emb_dim (0 = run-time P.D); the specialisations fully unroll the per-channel loops
+template <bool DBG, bool STATS, int DT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -417,7 +433,9 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   uint16_t* perm_s = (uint16_t*)(smem + P.off_perm);
   float2* znb = (float2*)(smem + P.off_zn);                 // [nst][128]: (bound on |z|, |z|^2)
 
-  const uint32_t zstage_bytes = (uint32_t)P.nD * TC_TILE * 128;
+  const int Dc = DT ? DT : P.D;                              // emb_dim
+  const int nD = DT ? (DT + TC_DCH - 1) / TC_DCH : P.nD;     // 32-channel chunks (zero-padded by TMA)
+  const uint32_t zstage_bytes = (uint32_t)nD * TC_TILE * 128;
   const int ktot = P.nb * P.BN;
 
   if (threadIdx.x == 32) {
@@ -460,11 +478,11 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      const uint32_t ebytes = (uint32_t)P.nb * P.nD * P.BN * 128 + (uint32_t)P.nb * P.BN * 32;
+      const uint32_t ebytes = (uint32_t)P.nb * nD * P.BN * 128 + (uint32_t)P.nb * P.BN * 32;
       mbar_expect_tx(BAR(0), ebytes);
       for (int blk = 0; blk < P.nb; ++blk)
-        for (int c = 0; c < P.nD; ++c)
-          tma_load_2d(sbase + P.off_emain + (uint32_t)(blk * P.nD + c) * P.BN * 128, &emap, BAR(0), c * TC_DCH, blk * P.BN);
+        for (int c = 0; c < nD; ++c)
+          tma_load_2d(sbase + P.off_emain + (uint32_t)(blk * nD + c) * P.BN * 128, &emap, BAR(0), c * TC_DCH, blk * P.BN);
       bulk_load_1d(sbase + P.off_eaug, P.eaug_img, (uint32_t)P.nb * P.BN * 32, BAR(0));
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -472,7 +490,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         mbar_wait_sleep(BAR(3 + s), ph ^ 1, 128);
         mbar_expect_tx(BAR(1 + s), zstage_bytes);
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
-        for (int c = 0; c < P.nD; ++c)
+        for (int c = 0; c < nD; ++c)
           for (int grp = 0; grp < 4; ++grp)    // one 32-pixel x 32-channel box per swizzle atom column
             tma_load_3d(sbase + P.off_z + s * zstage_bytes + c * (TC_TILE * 128) + grp * 4096, &zmap, BAR(1 + s),
                         pt * TC_TILE + grp * 32, c * TC_DCH, b);
@@ -495,9 +513,9 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
           uint32_t acc = 0;
-          for (int c = 0; c < P.nD; ++c) {
-            const int ksteps = min(4, (P.D - c * TC_DCH + 7) >> 3);
-            const uint32_t eaddr = sbase + P.off_emain + (uint32_t)(blk * P.nD + c) * P.BN * 128;
+          for (int c = 0; c < nD; ++c) {
+            const int ksteps = min(4, (Dc - c * TC_DCH + 7) >> 3);
+            const uint32_t eaddr = sbase + P.off_emain + (uint32_t)(blk * nD + c) * P.BN * 128;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t ad = make_desc(zaddr + c * (TC_TILE * 128) + ks * 1024, 4096, 512, 1);
               const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
@@ -518,7 +536,6 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     // ===================================== |z|^2 workers ====================================
     // two warps, two pixels per lane; same ascending-d fma chain as the CUDA-core kernels
     const int pA = (warp - 2) * 64 + lane;                // second pixel: pA + 32 (same swizzle phase)
-    const int nq = P.D >> 2;
     const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
     uint32_t zx[4];
 #pragma unroll
@@ -526,16 +543,20 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % P.nst, ph = (it / P.nst) & 1;
       mbar_wait(BAR(1 + s), ph);
-      const uint32_t zrow = zrow0 + s * zstage_bytes;
+      uint32_t zc = zrow0 + s * zstage_bytes;
       float za = 0.f, zb = 0.f;
-      for (int j = 0; j < nq; ++j) {
-        const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float va = lds_f32(zj + zx[i]), vb = lds_f32(zj + 4096 + zx[i]);
-          za = __fmaf_rn(va, va, za);
-          zb = __fmaf_rn(vb, vb, zb);
+      for (int c = 0; c < nD; ++c) {                      // channels beyond D are zero-filled by TMA: no guards
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float va = lds_f32(zc + jj * 512 + zx[i]), vb = lds_f32(zc + jj * 512 + 4096 + zx[i]);
+            za = __fmaf_rn(va, va, za);
+            zb = __fmaf_rn(vb, vb, zb);
+          }
         }
+        zc += 16384;
       }
       znb[s * TC_TILE + pA] = make_float2(sqrtf(za) * 1.00001f, za);
       znb[s * TC_TILE + pA + 32] = make_float2(sqrtf(zb) * 1.00001f, zb);
@@ -567,16 +588,20 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     const uint32_t win_s = sbase + P.off_win + (uint32_t)p * 4;
     const uint32_t perm_a = sbase + P.off_perm;
     float* sums_mine = nullptr;
-    if (P.sums) {
+    if (STATS) {
       const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
-      sums_mine = (rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * P.D) + 4 * cg;
+      sums_mine = (rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * Dc) + 4 * cg;
     }
     const size_t hw = (size_t)P.HW;
-    const size_t img_stride = (size_t)P.D * hw;
+    const size_t img_stride = (size_t)Dc * hw;
     float lsum = 0.f;
     int g = 0;
     int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile -> (image, tile in image)
     mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
+#ifdef VQ_TC_TIMING
+    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
     for (int it = 0; it < my_tiles; ++it) {
       const int s = P.nst == 2 ? (it & 1) : 0, ph = P.nst == 2 ? ((it >> 1) & 1) : (it & 1);
       const int b = tb, p0 = tpt * TC_TILE;
@@ -588,6 +613,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       mbar_wait(BAR(1 + s), ph);
       float zn, z2;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(zn), "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 8));
+      TC_TICK(0);
       const bool bad = !(z2 <= 3.0e38f);
       const uint32_t bestc = best_s + (uint32_t)(it & 1) * (TC_TILE * 8);   // this tile's slots; the other half is reset below
       if (DBG && cg == 0) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
@@ -613,7 +639,9 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       uint32_t rm0 = 0, rm1 = 0;
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
+        TC_TICK(1);
         mbar_wait(BAR(5 + a), aph);
+        TC_TICK(9);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
         for (int c = cg; c < nchunks; c += TC_NCG) {
@@ -664,6 +692,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         if (lane == 0) mbar_arrive(BAR(7 + a));
       }
 
+      TC_TICK(1);
       // ---- merge the column groups of each pixel ------------------------------------------------
       if (cnt < 2) rm1 = 0;
       if (cnt < 1) rm0 = 0;
@@ -674,6 +703,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
                      "r"(__float_as_uint(L)), "r"(w1) : "memory");
       }
       quad_bar(quad);                                     // (A) everybody's (L, U, count) is published
+      TC_TICK(2);
       if (cg == 0)                                        // next tile's slot: its last readers passed (A)
         asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(best_s + (uint32_t)((it + 1) & 1) * (TC_TILE * 8) + (uint32_t)p * 8), "r"(0u) : "memory");
       uint32_t pw[TC_NCG];
@@ -726,35 +756,50 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
       }
       quad_bar(quad);                                     // (C) winners of single-candidate pixels and the work list are visible
+      TC_TICK(3);
       const int nitems = min(wl_count[quad], TC_WLCAP);
+#ifdef VQ_TC_TIMING
+      tacc[7] += nitems;
+#endif
       if (nitems > 0) {
         // ---- exact fp32 re-rank of the listed (pixel, code) pairs ----------------------------------
         // One warp of the quadrant (rotating), one lane per pair: the dot product is the same ascending-d fma
         // chain as in the CUDA-core kernels (which reproduces the reference's fp32 GEMM for these sizes).
         if (cg == (it & (TC_NCG - 1))) {
-          const int nq = P.D >> 2;
           for (int i = lane; i < nitems; i += 32) {
             uint32_t item;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
             const int pp = (int)(item >> 16), k = (int)(item & 0xFFFFu);
             const int kb = k >> bnsh, row = k & (P.BN - 1);
-            uint32_t eb = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
-            const uint32_t r7 = (uint32_t)(row & 7);
+            uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
+            const uint32_t r7 = (uint32_t)(row & 7) << 4;
             uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
-            const uint32_t xs = (uint32_t)((pp & 31) >> 2);
-            const uint32_t x0 = xs << 4, x1 = 128 + ((xs ^ 2u) << 4), x2 = 256 + ((xs ^ 4u) << 4), x3 = 384 + ((xs ^ 6u) << 4);
+            const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
+            const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
             float dot = 0.f;
-            for (int j0 = 0; j0 < nq; j0 += 8) {            // one 32-channel chunk per iteration
-              const int jn = min(8, nq - j0);
-              for (int jj = 0; jj < jn; ++jj) {
-                const float4 e4 = lds_v4(eb + ((((uint32_t)jj) ^ r7) << 4));
-                const uint32_t zj = zr + (uint32_t)jj * 512;
-                dot = __fmaf_rn(lds_f32(zj + x0), e4.x, dot);
-                dot = __fmaf_rn(lds_f32(zj + x1), e4.y, dot);
-                dot = __fmaf_rn(lds_f32(zj + x2), e4.z, dot);
-                dot = __fmaf_rn(lds_f32(zj + x3), e4.w, dot);
+#pragma unroll
+            for (int c = 0; c < nD; ++c) {                  // zero-padded chunks: no guards
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {              // four quads' loads, then their sixteen chained fmas
+                float4 e4[4];
+                float zv[4][4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const int jj = hb * 4 + t;
+                  e4[t] = lds_v4(eb + (((uint32_t)jj << 4) ^ r7));
+                  const uint32_t zo = (uint32_t)c * 16384 + (uint32_t)jj * 512;
+                  zv[t][0] = lds_f32(x0 + zo); zv[t][1] = lds_f32(x1 + zo);
+                  zv[t][2] = lds_f32(x2 + zo); zv[t][3] = lds_f32(x3 + zo);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
+                  dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
+                  dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
+                  dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
+                }
               }
-              eb += bn128; zr += 16384;
+              eb += bn128;
             }
             uint32_t korig;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
@@ -768,9 +813,11 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
             atomicMax((unsigned long long*)(smem + P.off_best) + (it & 1) * TC_TILE + pp, key);
           }
         }
+        TC_TICK(8);
         quad_bar(quad);                                   // (D) all pairs of this quadrant are scored
         if (cg == 0 && lane == 0) wl_count[quad] = 0;
       }
+      TC_TICK(4);
       int w = 0;
       if (!fb) {
         if (total == 1) {
@@ -783,6 +830,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
       }
 
+      TC_TICK(10);
       // ---- outputs: ids, q, (z-q)^2, EMA statistics (channel quads j == cg mod TC_NCG) ------------
       const int pp = p0 + p;
       if (fb) {
@@ -800,51 +848,59 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           const size_t nb_ = (size_t)b * hw;
           if (P.ids) P.ids[nb_ + (size_t)(wc * P.H + h)] = (int64_t)worig;
           if (P.ids_nat) P.ids_nat[nb_ + pp] = (int)worig;
-          if (P.counts) atomicAdd(&hist[worig], 1);
+          if (STATS) atomicAdd(&hist[worig], 1);
         }
+        TC_TICK(11);
         const int kb = w >> bnsh, row = w & (P.BN - 1);
         const uint32_t r7 = (uint32_t)(row & 7);
-        // two quads per 32-channel chunk for this thread: jj = cg and cg + 4
-        uint32_t ea = emain + (uint32_t)(kb * P.nD) * bn128 + (uint32_t)row * 128;
-        uint32_t za = zrow + (uint32_t)cg * 512;
+        // two quads per 32-channel chunk for this thread (jj = cg and cg + 4); their shared-memory loads are issued
+        // together, before the first dependent instruction
+        uint32_t ea = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
+        const uint32_t za = zrow + (uint32_t)cg * 512;
         const uint32_t eo0 = (((uint32_t)cg ^ r7) << 4), eo1 = ((((uint32_t)cg + 4) ^ r7) << 4);
-        float* qo = P.q ? P.q + (size_t)b * img_stride + (size_t)(4 * cg) * hw + pp : nullptr;
-        float* so = sums_mine ? sums_mine + (size_t)worig * P.D : nullptr;
-        int d0 = 4 * cg;                                  // first channel of this thread's quad in the current chunk
-        for (int ci = 0; ci < P.nD; ++ci) {
+        float* qo = P.q + (size_t)b * img_stride + (size_t)(4 * cg) * hw + pp;
+        float* so = STATS ? sums_mine + (size_t)worig * Dc : nullptr;
+        constexpr bool kFull = DT != 0 && DT % TC_DCH == 0;   // every chunk complete: no channel guards
 #pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            if (d0 + 16 * hq < P.D) {
-              const float4 e4 = lds_v4(ea + (hq ? eo1 : eo0));
-              const uint32_t zj = za + (uint32_t)hq * 2048;
-              const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
-              float df = z0 - e4.x; lsum = __fmaf_rn(df, df, lsum);
-              df = z1 - e4.y; lsum = __fmaf_rn(df, df, lsum);
-              df = z2v - e4.z; lsum = __fmaf_rn(df, df, lsum);
-              df = z3 - e4.w; lsum = __fmaf_rn(df, df, lsum);
-              if (qo) {
-                float* qj = qo + (size_t)(16 * hq) * hw;
-                __stcs(qj, e4.x);
-                __stcs(qj + hw, e4.y);
-                __stcs(qj + 2 * hw, e4.z);
-                __stcs(qj + 3 * hw, e4.w);
-              }
-              if (so) atomicAdd(reinterpret_cast<float4*>(so + 16 * hq), make_float4(z0, z1, z2v, z3));
+        for (int ci = 0; ci < nD; ++ci) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (kFull || ci * 32 + 4 * cg + 16 * t < Dc) {
+              const float4 e4 = lds_v4(ea + (t ? eo1 : eo0));
+              const uint32_t zj = za + (uint32_t)ci * 16384 + (uint32_t)t * 2048;
+              float zv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) zv[i] = lds_f32(zj + zx[i]);
+              float df = zv[0] - e4.x; lsum = __fmaf_rn(df, df, lsum);
+              df = zv[1] - e4.y; lsum = __fmaf_rn(df, df, lsum);
+              df = zv[2] - e4.z; lsum = __fmaf_rn(df, df, lsum);
+              df = zv[3] - e4.w; lsum = __fmaf_rn(df, df, lsum);
+              float* qj = qo + (size_t)(32 * ci + 16 * t) * hw;
+              __stcs(qj, e4.x);
+              __stcs(qj + hw, e4.y);
+              __stcs(qj + 2 * hw, e4.z);
+              __stcs(qj + 3 * hw, e4.w);
+              if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 32 * ci + 16 * t), make_float4(zv[0], zv[1], zv[2], zv[3]));
             }
           }
-          ea += bn128; za += 16384; d0 += 32;
-          if (qo) qo += 32 * hw;
-          if (so) so += 32;
+          ea += bn128;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(3 + s));             // z stage free
+      TC_TICK(5);
     }
+#ifdef VQ_TC_TIMING
+    if (lane == 0 && blockIdx.x < 148) {
+      tacc[6] = my_tiles;
+      for (int i = 0; i < 16; ++i) g_tc_timing[((size_t)blockIdx.x * TC_EPI_WARPS + (warp - TC_AUX_WARPS)) * 16 + i] = tacc[i];
+    }
+#endif
     // ---- per-CTA reductions ------------------------------------------------------------------
     lsum = warp_sum(lsum);
     if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
     asm volatile("bar.sync 5, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");        // all epilogue warps
-    if (P.counts) {
+    if (STATS) {
       for (int k = threadIdx.x - 32 * TC_AUX_WARPS; k < P.K; k += 32 * TC_EPI_WARPS) {
         const int c = hist[k];
         if (c) atomicAdd(&P.counts[k], c);
@@ -893,6 +949,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
   const TcGeom g = tc_geometry(a.D, a.K);
   VQ_REQUIRE(g.ok && g.nb * g.BN <= TC_SORT_MAX && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
+  VQ_REQUIRE(a.q != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
   EncodeTiledFn enc = get_encode_fn();
   VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
@@ -953,11 +1010,17 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
 
   int grid = sm_count_tc();
   if (grid > P.ntiles) grid = P.ntiles;
-  auto kern = dbg ? vq_assign_tc_kernel<true> : vq_assign_tc_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[dbg ? 1 : 0]) {
+  const bool stats = a.stats != nullptr;
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const TcParams);
+  KernFn kern;
+  int ki;
+  if (dbg) { kern = stats ? vq_assign_tc_kernel<true, true, 0> : vq_assign_tc_kernel<true, false, 0>; ki = stats ? 1 : 0; }
+  else if (a.D == 64) { kern = stats ? vq_assign_tc_kernel<false, true, 64> : vq_assign_tc_kernel<false, false, 64>; ki = stats ? 3 : 2; }
+  else { kern = stats ? vq_assign_tc_kernel<false, true, 0> : vq_assign_tc_kernel<false, false, 0>; ki = stats ? 5 : 4; }
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  if (!attr_set[ki]) {
     VQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    attr_set[dbg ? 1 : 0] = true;
+    attr_set[ki] = true;
   }
   const bool prof = profile_begin(s);
   kern<<<grid, TC_THREADS, g.total, s>>>(zmap, emap, P);
@@ -968,6 +1031,18 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
 }
 
 int launch_assign_tc(const FwdArgs& a, cudaStream_t s) { return launch_assign_tc_impl(a, nullptr, s); }
+
+int tc_debug_timing(long long* host_out, int n) {
+#ifdef VQ_TC_TIMING
+  const int tot = 148 * TC_EPI_WARPS * 16;
+  if (n < tot) return -1;
+  if (cudaMemcpyFromSymbol(host_out, g_tc_timing, sizeof(long long) * tot) != cudaSuccess) return -2;
+  return tot;
+#else
+  (void)host_out; (void)n;
+  return 0;
+#endif
+}
 
 int tc_debug_ncols(int D, int K) {
   const TcGeom g = tc_geometry(D, K);

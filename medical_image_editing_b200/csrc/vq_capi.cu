@@ -48,7 +48,7 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
   a.ws = carve_workspace(workspace, N, K, D);
   cudaStream_t s = (cudaStream_t)stream;
 
-  bool use_tc = !(flags & VQ_FLAG_FORCE_SIMT) && tc_path_supported(B, D, H, W, K);
+  bool use_tc = !(flags & VQ_FLAG_FORCE_SIMT) && q != nullptr && tc_path_supported(B, D, H, W, K);
   if ((flags & VQ_FLAG_FORCE_TC) && !use_tc) {
     set_error("vq_assign_fwd: tensor-core path unsupported for B=%d D=%d H=%d W=%d K=%d", B, D, H, W, K);
     return VQ_ERR_UNSUPPORTED;
@@ -103,6 +103,8 @@ int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, f
 }
 
 int vq_debug_tc_ncols(int D, int K) { return tc_debug_ncols(D, K); }
+
+int vq_debug_tc_timing(long long* host_out, int n) { return tc_debug_timing(host_out, n); }
 
 int vq_debug_tc_scores(const float* z, int B, int D, int H, int W, const float* embed, int K, float* out,
                        void* workspace, size_t workspace_bytes, vq_stream_t stream) {

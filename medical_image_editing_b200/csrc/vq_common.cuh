@@ -107,6 +107,7 @@ int launch_assign_tc(const FwdArgs& a, cudaStream_t s);          // vq_assign_tc
 bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc.cu
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int tc_debug_ncols(int D, int K);
+int tc_debug_timing(long long* host_out, int n);
 int launch_fallback_rows(const FwdArgs& a, cudaStream_t s);
 int launch_finish(const FwdArgs& a, bool tc_path, cudaStream_t s);
 int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,

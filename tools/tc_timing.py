@@ -1,0 +1,51 @@
+"""Phase timing of the tensor-core epilogue.  Build first with
+   VQ_EXTRA_FLAGS=-DVQ_TC_TIMING FORCE=1 bash medical_image_editing_b200/csrc/build.sh
+then run on the GPU box:  python tools/tc_timing.py [D K B train]"""
+import ctypes
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import medical_image_editing_b200 as pkg
+
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+train = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
+H = 256
+dev = "cuda:0"
+g = torch.Generator(device=dev).manual_seed(1)
+L = pkg.lib()
+m = pkg.VQ(emb_dim=D, dict_size=K, momentum=0.99, eps=1e-5, knn_backend="torch").to(dev)
+with torch.no_grad():
+    m.cluster_size.fill_(2048.0)
+    m.embed_avg.copy_(m.embed.T * 2048.0)       # consistent EMA state: embed == embed_avg / cluster_size
+m.train(train)
+z = [torch.randn(B, D, H, H, device=dev, generator=g) for _ in range(3)]
+with torch.no_grad():
+    for i in range(3):
+        m(z[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m(z[0])
+    e1.record()
+    torch.cuda.synchronize()
+print("forward ms", e0.elapsed_time(e1))
+buf = np.zeros(148 * 16 * 16, dtype=np.int64)
+n = L.vq_debug_tc_timing(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+print("timing entries", n)
+if n > 0:
+    t = buf.reshape(148, 16, 16).astype(np.float64)
+    tiles = t[:, :, 6].mean()
+    names = ["wait z/zn", "scan", "merge(A)", "push(C)", "barrier D", "q/sums", "-", "-", "rerank work", "wait tmem", "decode", "ids/hist"]
+    tot = (t[:, :, :6].sum(axis=2) + t[:, :, 8:12].sum(axis=2)).mean()
+    print(f"re-rank pairs per quadrant and tile: mean {(t[:, :, 7] / t[:, :, 6]).mean():.2f} max {(t[:, :, 7] / t[:, :, 6]).max():.2f}")
+    print(f"tiles per CTA {tiles:.1f}; cycles per tile (mean over warps) {tot / tiles:.0f}")
+    for i, nm in enumerate(names):
+        if nm == '-':
+            continue
+        per = t[:, :, i] / t[:, :, 6]
+        print(f"  {nm:10s} mean {per.mean():8.0f}  min {per.min():8.0f}  max {per.max():8.0f}   by cg: " +
+              " ".join(f"{per.reshape(148, 4, 4)[:, c, :].mean():7.0f}" for c in range(4)))
