@@ -145,7 +145,7 @@ int vq_debug_tc_scores(const float* z, int B, int D, int H, int W, const float* 
                        void* workspace, size_t workspace_bytes, vq_stream_t stream);
 int vq_debug_fallback_rows(const void* workspace, int64_t N, int K, int D, vq_stream_t stream);
 /* Phase timing of the tensor-core epilogue (only in builds with -DVQ_TC_TIMING; returns 0 otherwise): HOST buffer of
- * 148*16*16 int64 clock sums [cta][epilogue warp][phase]. */
+ * 148*16*8 int64 clock sums [cta][scan warps 0-7, output warps 8-15][slot]. */
 int vq_debug_tc_timing(long long* host_out, int n);
 int vq_profile_enable(int on);
 int vq_profile_read(double* total_ms, int* launches);

@@ -34,19 +34,19 @@ namespace vqb200 {
 constexpr int TC_TILE = 128;        // pixels per tile (UMMA M)
 constexpr int TC_MAXBN = 256;       // codes per accumulator stage (UMMA N)
 constexpr int TC_DCH = 32;          // channels per shared-memory chunk (128-byte swizzle rows)
-constexpr int TC_NCG = 4;           // column groups: epilogue warps per TMEM lane quadrant
-constexpr int TC_EPI_WARPS = 4 * TC_NCG;
+constexpr int TC_NCG = 2;           // column groups: scan warps per TMEM lane quadrant
+constexpr int TC_SCAN_WARPS = 4 * TC_NCG;
+constexpr int TC_OUT_WARPS = 8;     // 16 pixels of the tile each
 constexpr int TC_AUX_WARPS = 4;     // TMA producer, MMA issuer, two |z|^2 workers
-constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_EPI_WARPS);
-constexpr int TC_WLCAP = 64;        // (pixel, code) pairs re-scored exactly per quadrant and tile
+constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_SCAN_WARPS + TC_OUT_WARPS);
+constexpr int TC_WLCAP = 32;        // (pixel, code) pairs re-scored exactly per output warp and tile
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SORT_MAX = 4096;     // codes the single-CTA sort of vq_tc_prep2_kernel handles
 constexpr int TC_MAX_REP = 32;        // replicas of the per-code sums (spreads the L2 reduction traffic)
 
 struct TcGeom {
   int BN, nb, nD, nst;
-  size_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_best, off_wl, off_zn, off_hist, off_perm,
-      off_ctab, off_bar, total;
+  size_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_wl, off_zn, off_hist, off_perm, off_ctab, off_bar, total;
   bool ok;
 };
 
@@ -66,19 +66,17 @@ static TcGeom tc_geometry(int D, int K) {
   g.off_eaug = off;  off += align_up(eaug, 1024);
   g.off_aaug = off;  off += 4096;
   g.off_z = off;
-  const size_t sz_pub = (size_t)TC_NCG * TC_TILE * 8, sz_win = TC_TILE * 4, sz_best = 2 * TC_TILE * 8;
-  const size_t sz_wl = 4 * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 8;
+  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16;     // [tile parity][column group][pixel] x 16 B
+  const size_t sz_wl = (size_t)TC_OUT_WARPS * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
   const size_t sz_hist = align_up((size_t)K * 4, 16), sz_perm = align_up(ktot * 2, 16);
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
-  const size_t tail = sz_pub + sz_win + sz_best + sz_wl + sz_zn + sz_hist + sz_perm + sz_ctab + 256;
+  const size_t tail = sz_pub + sz_wl + sz_zn + sz_hist + sz_perm + sz_ctab + 256;
   for (int nst = 2; nst >= 1; --nst) {
     if (off + nst * zstage + tail + 1024 <= (size_t)TC_SMEM_LIMIT) { g.nst = nst; g.ok = true; break; }
   }
   if (!g.ok) return g;
   off += g.nst * zstage;
   g.off_pub = off;  off += sz_pub;
-  g.off_win = off;  off += sz_win;
-  g.off_best = off; off += sz_best;
   g.off_wl = off;   off += sz_wl;
   g.off_zn = off;   off += sz_zn;
   g.off_hist = off; off += sz_hist;
@@ -362,8 +360,7 @@ struct TcParams {
   int bn_shift;           // BN == 1 << bn_shift
   int w_shift;            // W == 1 << w_shift, or -1
   int tiles_per_img; int ntiles;
-  uint32_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_best, off_wl, off_zn, off_hist, off_perm,
-      off_ctab, off_bar;
+  uint32_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_wl, off_zn, off_hist, off_perm, off_ctab, off_bar;
   int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
   float* sums;            // replica 0 of the per-code sums (inside the packed statistics buffer), or null
   float* sums_rep;        // replicas 1..nrep-1 (workspace), [nrep-1][K*D]
@@ -381,9 +378,6 @@ __device__ __forceinline__ uint32_t zs_off(int p, int d) {
                     ((((p & 31) >> 2) ^ ((row & 3) << 1)) << 4) + ((p & 3) << 2));
 }
 
-__device__ __forceinline__ void quad_bar(int quad) {      // the NCG warps that share one TMEM lane quadrant
-  asm volatile("bar.sync %0, %1;" ::"r"(quad + 1), "n"(32 * TC_NCG) : "memory");
-}
 __device__ __forceinline__ uint32_t f32_orderable(float x) {   // monotone map float -> uint32
   const uint32_t u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -395,21 +389,30 @@ __device__ __forceinline__ uint32_t f32_up16(float x) {
   return (u + 0xFFFFu) & 0xFFFF0000u;                        // positive: bump the magnitude (inf stays inf)
 }
 
-constexpr unsigned long long TC_KEY_FALLBACK = ~0ull;
-
-// Optional phase timing of the epilogue (build with -DVQ_TC_TIMING; read with vq_debug_tc_timing): clock64 deltas
-// summed over tiles by lane 0 of every epilogue warp.  Phases: 0 wait z | 1 scan | 2 merge (A) | 3 push (C) |
-// 4 re-rank (D) | 5 outputs | 6 tiles
+// Optional role timing (build with -DVQ_TC_TIMING; read with vq_debug_tc_timing): clock64 deltas summed over tiles by
+// lane 0 of every scan / output warp: [cta][warp 0..15][slot], slots: scan warps 0 wait |z|^2, 1 wait tmem, 2 scan work,
+// 3 wait pub slot, 4 publish ; output warps 0 wait z/|z|^2, 1 wait scan results, 2 merge, 3 pair list + re-rank,
+// 4 outputs ; slot 6 tiles, slot 7 pairs
 #ifdef VQ_TC_TIMING
-__device__ long long g_tc_timing[148 * TC_EPI_WARPS * 16];
+__device__ long long g_tc_timing[148 * 16 * 8];
+#define TC_TIMING_DECL long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tlast = clock64();
 #define TC_TICK(slot)                                                   \
   do {                                                                  \
     const long long _now = clock64();                                   \
     tacc[slot] += _now - tlast;                                         \
     tlast = _now;                                                       \
   } while (0)
+#define TC_TIMING_STORE(widx, ntiles_)                                                                   \
+  do {                                                                                                  \
+    if (lane == 0 && blockIdx.x < 148) {                                                                \
+      tacc[6] = (ntiles_);                                                                              \
+      for (int _i = 0; _i < 8; ++_i) g_tc_timing[((size_t)blockIdx.x * 16 + (widx)) * 8 + _i] = tacc[_i]; \
+    }                                                                                                   \
+  } while (0)
 #else
+#define TC_TIMING_DECL
 #define TC_TICK(slot) do { } while (0)
+#define TC_TIMING_STORE(widx, ntiles_) do { } while (0)
 #endif
 
 // DT: compile-time emb_dim (0 = run-time P.D); the specialisations fully unroll the per-channel loops
@@ -423,15 +426,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 
   uint64_t* bars = (uint64_t*)(smem + P.off_bar);
   const uint32_t bar0 = sbase + P.off_bar;
-  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty | 9,10 zn_full
-  // slot 11: tmem base ; slots 12,13: work-list counters of the four quadrants (4 x int)
+  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty | 9,10 zn_full |
+  //                11,12 pub_full | 13,14 pub_empty ; slot 15: tmem base
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
-  int* wl_count = (int*)(bars + 12);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
   int* hist = (int*)(smem + P.off_hist);
-  unsigned long long* best = (unsigned long long*)(smem + P.off_best);
   uint16_t* perm_s = (uint16_t*)(smem + P.off_perm);
-  float2* znb = (float2*)(smem + P.off_zn);                 // [nst][128]: (bound on |z|, |z|^2)
 
   const int Dc = DT ? DT : P.D;                              // emb_dim
   const int nD = DT ? (DT + TC_DCH - 1) / TC_DCH : P.nD;     // 32-channel chunks (zero-padded by TMA)
@@ -441,10 +441,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   if (threadIdx.x == 32) {
     mbar_init(BAR(0), 1);
     mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-    mbar_init(BAR(3), TC_EPI_WARPS + 2); mbar_init(BAR(4), TC_EPI_WARPS + 2);
+    mbar_init(BAR(3), TC_OUT_WARPS + 2); mbar_init(BAR(4), TC_OUT_WARPS + 2);
     mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-    mbar_init(BAR(7), TC_EPI_WARPS); mbar_init(BAR(8), TC_EPI_WARPS);
+    mbar_init(BAR(7), TC_SCAN_WARPS); mbar_init(BAR(8), TC_SCAN_WARPS);
     mbar_init(BAR(9), 2); mbar_init(BAR(10), 2);
+    mbar_init(BAR(11), TC_SCAN_WARPS); mbar_init(BAR(12), TC_SCAN_WARPS);
+    mbar_init(BAR(13), TC_OUT_WARPS); mbar_init(BAR(14), TC_OUT_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -453,8 +455,8 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   }
   if (warp >= TC_AUX_WARPS) {
     // ones block of the augmentation K-step: 4 groups x 8 rows x 128 B; rows 0..2 = 1, rows 3..7 = 0
-    const int t = threadIdx.x - 32 * TC_AUX_WARPS;        // 0 .. 32*TC_EPI_WARPS-1
-    constexpr int NT = 32 * TC_EPI_WARPS;
+    const int t = threadIdx.x - 32 * TC_AUX_WARPS;
+    constexpr int NT = 32 * (TC_SCAN_WARPS + TC_OUT_WARPS);
     float4* a = (float4*)(smem + P.off_aaug);
     for (int i = t; i < 256; i += NT) {                   // 256 float4 = 4 KB
       const int row = (i >> 3) & 7;
@@ -464,8 +466,6 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     for (int k = t; k < P.K; k += NT) hist[k] = 0;
     for (int k = t; k < ktot; k += NT) perm_s[k] = (uint16_t)P.perm[k];
     for (int c = t; c < 2 * P.nb * (P.BN >> 5); c += NT) ((float*)(smem + P.off_ctab))[c] = P.ctab[c];
-    if (t < 4) wl_count[t] = 0;
-    for (int i = t; i < 2 * TC_TILE; i += NT) best[i] = 0ull;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -474,6 +474,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool two_stages = P.nst == 2;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -486,7 +487,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       bulk_load_1d(sbase + P.off_eaug, P.eaug_img, (uint32_t)P.nb * P.BN * 32, BAR(0));
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
-        const int s = it % P.nst, ph = (it / P.nst) & 1;
+        const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
         mbar_wait_sleep(BAR(3 + s), ph ^ 1, 128);
         mbar_expect_tx(BAR(1 + s), zstage_bytes);
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
@@ -503,7 +504,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       mbar_wait(BAR(0), 0);
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % P.nst, ph = (it / P.nst) & 1;
+        const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
         mbar_wait_sleep(BAR(1 + s), ph, 32);
         tc_fence_after();
         const uint32_t zaddr = sbase + P.off_z + s * zstage_bytes;
@@ -537,11 +538,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     // two warps, two pixels per lane; same ascending-d fma chain as the CUDA-core kernels
     const int pA = (warp - 2) * 64 + lane;                // second pixel: pA + 32 (same swizzle phase)
     const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
+    const uint32_t zn_s = sbase + P.off_zn;
     uint32_t zx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((pA & 31) >> 2) ^ (i << 1)) << 4);
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % P.nst, ph = (it / P.nst) & 1;
+      const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(BAR(1 + s), ph);
       uint32_t zc = zrow0 + s * zstage_bytes;
       float za = 0.f, zb = 0.f;
@@ -558,101 +560,57 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
         zc += 16384;
       }
-      znb[s * TC_TILE + pA] = make_float2(sqrtf(za) * 1.00001f, za);
-      znb[s * TC_TILE + pA + 32] = make_float2(sqrtf(zb) * 1.00001f, zb);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(zn_s + (uint32_t)(s * TC_TILE + pA) * 4), "f"(za) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(zn_s + (uint32_t)(s * TC_TILE + pA + 32) * 4), "f"(zb) : "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(BAR(9 + s)); mbar_arrive(BAR(3 + s)); }
     }
-  } else {
-    // ===================================== epilogue =========================================
-    // warp = (quad, cg): TMEM lane quadrant `quad` (pixels quad*32 .. +31), column group cg: scans the 32-code
-    // chunks c == cg (mod TC_NCG) of every block, then handles the channel quads j == cg (mod TC_NCG) of its pixel.
+  } else if (warp < TC_AUX_WARPS + TC_SCAN_WARPS) {
+    // ===================================== scan warps =======================================
+    // warp = (TMEM lane quadrant, column group): thread = (pixel, half of the 32-code chunks).  Running max and
+    // sign-bit candidate masks over the accumulators; the result (bounds + <= 2 candidate chunks) is published in
+    // shared memory for the output warps.  No exact arithmetic, no synchronisation with sibling warps.
     const int quad = warp & 3, cg = (warp - TC_AUX_WARPS) >> 2;
     const int p = quad * 32 + lane;                       // pixel within the tile == TMEM lane
-    const float rminbig = P.meta[1];
     const uint32_t ctab_s = sbase + P.off_ctab;
+    const uint32_t zn_s = sbase + P.off_zn + (uint32_t)p * 4;
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)(cg * TC_TILE + p) * 16;
     const int nchunks = P.BN >> 5;
-    const int ncols = ktot;
-    const int bnsh = P.bn_shift;                          // BN == 1 << bnsh
-    const uint32_t bn128 = (uint32_t)P.BN * 128;
-    // shared-memory address of z(p, d) = zrow + (d>>5)*16384 + (d&31)*128 + zx[d&3]   (see zs_off)
-    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
-    uint32_t zx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
-    const uint32_t emain = sbase + P.off_emain;
-    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 8;                  // [TC_NCG][128] uint2, this pixel's column
-    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)quad * (TC_WLCAP * 4);   // this quadrant's work list
-    const uint32_t zn_s = sbase + P.off_zn;
-    const uint32_t best_s = sbase + P.off_best;
-    const uint32_t win_s = sbase + P.off_win + (uint32_t)p * 4;
-    const uint32_t perm_a = sbase + P.off_perm;
-    float* sums_mine = nullptr;
-    if (STATS) {
-      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
-      sums_mine = (rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * Dc) + 4 * cg;
-    }
-    const size_t hw = (size_t)P.HW;
-    const size_t img_stride = (size_t)Dc * hw;
-    float lsum = 0.f;
     int g = 0;
-    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile -> (image, tile in image)
-    mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
-#ifdef VQ_TC_TIMING
-    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long tlast = clock64();
-#endif
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // only for the debug dump
+    TC_TIMING_DECL
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = P.nst == 2 ? (it & 1) : 0, ph = P.nst == 2 ? ((it >> 1) & 1) : (it & 1);
-      const int b = tb, p0 = tpt * TC_TILE;
-      tpt += (int)gridDim.x;
-      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
-      const uint32_t zst = s * zstage_bytes;
-      const uint32_t zrow = zrow0 + zst;
-      mbar_wait(BAR(9 + s), ph);                          // |z|^2 ready (implies the z tile landed)
-      mbar_wait(BAR(1 + s), ph);
-      float zn, z2;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(zn), "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 8));
+      const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
+      TC_TICK(4);
+      mbar_wait(BAR(9 + s), ph);                          // |z|^2 of this tile
       TC_TICK(0);
-      const bool bad = !(z2 <= 3.0e38f);
-      const uint32_t bestc = best_s + (uint32_t)(it & 1) * (TC_TILE * 8);   // this tile's slots; the other half is reset below
-      if (DBG && cg == 0) {   // second debug area (after the accumulators): what the epilogue sees in shared memory
-        float* o2 = P.dbg + (size_t)P.B * P.HW * ncols + ((size_t)b * P.HW + p0 + p) * 8;
-        const uint8_t* zs = smem + P.off_z + zst;
-        const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
-        o2[0] = z2;
-        o2[1] = *(const float*)(zs + zs_off(p, 0));
-        o2[2] = *(const float*)(zs + zs_off(p, 1));
-        o2[3] = *(const float*)(eb0 + ((0 ^ (p & 7)) << 4));                             // E[p][0]
-        o2[4] = *(const float*)(eb0 + ((1 ^ (p & 7)) << 4) + 4);                         // E[p][5]
-        o2[5] = *(const float*)(smem + P.off_eaug + (p >> 3) * 256 + (p & 7) * 16);      // aug[p][0]
-        o2[6] = *(const float*)(smem + P.off_aaug + p * 4);
-        o2[7] = __uint_as_float(tmem_base);
-      }
-      // ---- scan: this warp's chunks of every block -------------------------------------------
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)s * (TC_TILE * 4)));
+      const float zn = sqrtf(z2) * 1.00001f;
       // Running state (accumulator units, a_k = z.e_k - |e_k|^2/2):
       //   L     lower bound on the best exact a_k among the columns this thread has seen = max_c (chunkmax_c - delta_c)
       //   Urec  upper bound on the exact a_k of every recorded candidate
       // A column of chunk c is a candidate iff approx + delta_c >= L, i.e. approx >= L - delta_c.
       float L = -INFINITY, Urec = -INFINITY;
-      int cnt = 0, rc0 = 0, rc1 = 0;                      // records: first column of the chunk, candidate mask
-      uint32_t rm0 = 0, rm1 = 0;
+      int cnt = 0;
+      uint32_t rcA = 0, rcB = 0, rm0 = 0, rm1 = 0;        // records: global chunk index, candidate mask
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
-        TC_TICK(1);
+        TC_TICK(2);
         mbar_wait(BAR(5 + a), aph);
-        TC_TICK(9);
+        TC_TICK(1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
         for (int c = cg; c < nchunks; c += TC_NCG) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
+          const int gc = blk * nchunks + c;               // global chunk index (sorted codes gc*32 .. gc*32+31)
           float cA, cB;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)(blk * nchunks + c) * 8));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)gc * 8));
           const float delta = __fmaf_rn(zn, cA, cB);
           tmem_ld_wait();
           if (DBG) {
-            float* o = P.dbg + ((size_t)b * P.HW + p0 + p) * ncols + blk * P.BN + c * 32;
+            float* o = P.dbg + ((size_t)tb * P.HW + tpt * TC_TILE + p) * ktot + gc * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = v[j];
           }
@@ -681,9 +639,8 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           // branch-free record update
           const bool has = cand != 0u;
           const bool s0 = has && cnt == 0, s1 = has && cnt == 1;
-          const int col = (blk << bnsh) + c * 32;
-          rc0 = s0 ? col : rc0; rm0 = s0 ? cand : rm0;
-          rc1 = s1 ? col : rc1; rm1 = s1 ? cand : rm1;
+          rcA = s0 ? (uint32_t)gc : rcA; rm0 = s0 ? cand : rm0;
+          rcB = s1 ? (uint32_t)gc : rcB; rm1 = s1 ? cand : rm1;
           cnt += has ? 1 : 0;
           Urec = has ? fmaxf(Urec, cm + delta) : Urec;
         }
@@ -691,37 +648,106 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(7 + a));
       }
-
-      TC_TICK(1);
-      // ---- merge the column groups of each pixel ------------------------------------------------
+      if (DBG && cg == 0) {   // second debug area (after the accumulators): what the warps see in shared memory
+        float* o2 = P.dbg + (size_t)P.B * P.HW * ktot + ((size_t)tb * P.HW + tpt * TC_TILE + p) * 8;
+        const uint8_t* zs = smem + P.off_z + s * zstage_bytes;
+        const uint8_t* eb0 = smem + P.off_emain + (size_t)p * 128;                       // code p of block 0, chunk 0
+        o2[0] = z2;
+        o2[1] = *(const float*)(zs + zs_off(p, 0));
+        o2[2] = *(const float*)(zs + zs_off(p, 1));
+        o2[3] = *(const float*)(eb0 + ((0 ^ (p & 7)) << 4));                             // E[p][0]
+        o2[4] = *(const float*)(eb0 + ((1 ^ (p & 7)) << 4) + 4);                         // E[p][5]
+        o2[5] = *(const float*)(smem + P.off_eaug + (p >> 3) * 256 + (p & 7) * 16);      // aug[p][0]
+        o2[6] = *(const float*)(smem + P.off_aaug + p * 4);
+        o2[7] = __uint_as_float(tmem_base);
+      }
+      if (DBG) { tpt += (int)gridDim.x; while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; } }
+      // ---- publish: {L, U16 | chunkA<<8 | chunkB<<1 | overflow, maskA, maskB} -------------------------------
       if (cnt < 2) rm1 = 0;
       if (cnt < 1) rm0 = 0;
-      const uint32_t nC = (uint32_t)(__popc(rm0) + __popc(rm1));
-      {
-        const uint32_t w1 = f32_up16(Urec) | (cnt > 2 ? 0x100u : 0u) | nC;   // nC <= 64
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(pub_s + (uint32_t)cg * (TC_TILE * 8)),
-                     "r"(__float_as_uint(L)), "r"(w1) : "memory");
-      }
-      quad_bar(quad);                                     // (A) everybody's (L, U, count) is published
+      const uint32_t w1 = f32_up16(Urec) | (rcA << 8) | (rcB << 1) | (cnt > 2 ? 1u : 0u);   // chunk indices < 128
+      const int par = it & 1, pph = (it >> 1) & 1;
       TC_TICK(2);
-      if (cg == 0)                                        // next tile's slot: its last readers passed (A)
-        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(best_s + (uint32_t)((it + 1) & 1) * (TC_TILE * 8) + (uint32_t)p * 8), "r"(0u) : "memory");
-      uint32_t pw[TC_NCG];
+      mbar_wait(BAR(13 + par), pph ^ 1);                  // the output warps are done with this slot (tile it-2)
+      TC_TICK(3);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_s + (uint32_t)par * (TC_NCG * TC_TILE * 16)),
+                   "r"(__float_as_uint(L)), "r"(w1), "r"(rm0), "r"(rm1) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(11 + par));
+    }
+    TC_TIMING_STORE(warp - TC_AUX_WARPS, my_tiles);
+  } else {
+    // ===================================== output warps =====================================
+    // warp ow owns pixels 16*ow .. 16*ow+15 of the tile; lane = (pixel px, channel half hf): all decisions for a
+    // pixel are taken inside one warp.  Per tile: merge the scan warps' bounds -> single candidate or a list of
+    // (pixel, code) pairs -> exact fp32 re-rank of the pairs (one lane per pair, ascending-d fma chain) -> ids, q,
+    // (z-q)^2, EMA statistics for the channel quads j == hf (mod 2).
+    const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
+    const int px = lane & 15, hf = lane >> 4;
+    const int p = ow * 16 + px;                           // pixel within the tile
+    const float rminbig = P.meta[1];
+    const int bnsh = P.bn_shift;                          // BN == 1 << bnsh
+    const uint32_t bn128 = (uint32_t)P.BN * 128;
+    const int nq = Dc >> 2;
+    // shared-memory address of z(p, d) = zrow + (d>>5)*16384 + (d&31)*128 + zx[d&3]   (see zs_off)
+    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
+    const uint32_t emain = sbase + P.off_emain;
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
+    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TC_WLCAP * 4);     // this warp's pair list
+    const uint32_t zn_s = sbase + P.off_zn;
+    const uint32_t perm_a = sbase + P.off_perm;
+    float* sums_mine = nullptr;
+    if (STATS) {
+      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
+      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * Dc;
+    }
+    const size_t hw = (size_t)P.HW;
+    const size_t img_stride = (size_t)Dc * hw;
+    float lsum = 0.f;
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile -> (image, tile in image)
+    mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
+    TC_TIMING_DECL
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
+      const int par = it & 1, pph = (it >> 1) & 1;
+      const int b = tb, p0 = tpt * TC_TILE;
+      tpt += (int)gridDim.x;
+      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
+      const uint32_t zst = s * zstage_bytes;
+      const uint32_t zrow = zrow0 + zst;
+      TC_TICK(4);
+      mbar_wait(BAR(1 + s), ph);                          // z tile (TMA writes) visible to this thread
+      mbar_wait(BAR(9 + s), ph);                          // |z|^2
+      TC_TICK(0);
+      mbar_wait(BAR(11 + par), pph);                      // scan results of this tile
+      TC_TICK(1);
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 4));
+      const float zn = sqrtf(z2) * 1.00001f;
+      const bool bad = !(z2 <= 3.0e38f);
+
+      // ---- merge the column groups of the pixel ---------------------------------------------------
+      uint32_t pw[TC_NCG][4];
       float Lg = -INFINITY;
 #pragma unroll
       for (int i = 0; i < TC_NCG; ++i) {
-        uint32_t l;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(pw[i]) : "r"(pub_s + (uint32_t)i * (TC_TILE * 8)));
-        Lg = fmaxf(Lg, __uint_as_float(l));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pw[i][0]), "=r"(pw[i][1]), "=r"(pw[i][2]), "=r"(pw[i][3])
+                     : "r"(pub_s + (uint32_t)(par * TC_NCG + i) * (TC_TILE * 16)));
+        Lg = fmaxf(Lg, __uint_as_float(pw[i][0]));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(13 + par));          // the slot may be overwritten (tile it+2)
       int total = 0;
-      bool ovf = false, alive = false;
+      bool ovf = false;
 #pragma unroll
       for (int i = 0; i < TC_NCG; ++i) {
-        const bool al = __uint_as_float(pw[i] & 0xFFFF0000u) >= Lg;
-        total += al ? (int)(pw[i] & 0xFFu) : 0;
-        ovf |= al && (pw[i] & 0x100u) != 0;
-        if (i == cg) alive = al;
+        const bool al = __uint_as_float(pw[i][1] & 0xFFFF0000u) >= Lg;
+        if (!al) { pw[i][2] = 0; pw[i][3] = 0; }
+        else ovf |= (pw[i][1] & 1u) != 0;
+        total += __popc(pw[i][2]) + __popc(pw[i][3]);
       }
       const float lbest = 2.f * Lg;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
       // excluded ("big") codes: s_k <= r_k (2|z| - r_k), decreasing in r_k for r_k >= |z|
@@ -731,49 +757,65 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         big_safe = (rminbig >= zn) && (bigub + 1e-5f * (fabsf(bigub) + fabsf(lbest)) < lbest);
       }
       bool fb = bad || ovf || total == 0 || !big_safe;
-      if (!fb && alive) {
-        if (total == 1) {
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s), "r"(rc0 + __clz(rm0)) : "memory");   // nC == 1 => record 0
-        } else {
-          const int slot = atomicAdd(&wl_count[quad], (int)nC);
-          // pairs that do not fit send the pixel to the exhaustive search; the slots below the capacity are
-          // still filled so that every listed pair is valid
-          if (slot + (int)nC > TC_WLCAP)
-            atomicMax((unsigned long long*)(smem + P.off_best) + (it & 1) * TC_TILE + p, TC_KEY_FALLBACK);
-          uint32_t wa = wl_s + (uint32_t)slot * 4;
-          const uint32_t wend = wl_s + TC_WLCAP * 4;
+      int w = 0;                                          // winner: position in the norm-sorted codebook
+      if (total == 1) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            uint32_t m = r ? rm1 : rm0;
-            const uint32_t base = ((uint32_t)p << 16) | (uint32_t)(r ? rc1 : rc0);
-            while (m && wa < wend) {
-              const int jb = __clz(m);
-              m &= ~(0x80000000u >> jb);
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
-              wa += 4;
+        for (int i = 0; i < TC_NCG; ++i) {
+          if (pw[i][2]) w = (int)(((pw[i][1] >> 8) & 0x7Fu) * 32u) + __clz(pw[i][2]);
+          if (pw[i][3]) w = (int)(((pw[i][1] >> 1) & 0x7Fu) * 32u) + __clz(pw[i][3]);
+        }
+      }
+      TC_TICK(2);
+      // ---- pixels with several candidates: (pixel, code) pairs -> exact re-rank ------------------------
+      const int mine = (!fb && total > 1 && hf == 0) ? total : 0;      // pairs this lane contributes
+      int pos = mine;                                                   // inclusive prefix sum over the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += t;
+      }
+      const int npairs = __shfl_sync(0xffffffffu, pos, 31);
+      pos -= mine;                                                      // exclusive
+      if (npairs > 0) {
+        if (mine > 0) {
+          if (pos + mine > TC_WLCAP) {
+            fb = true;                                    // list full: exhaustive search for this pixel
+          } else {
+            uint32_t wa = wl_s + (uint32_t)pos * 4;
+#pragma unroll
+            for (int i = 0; i < TC_NCG; ++i) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                uint32_t m = pw[i][2 + r];
+                const uint32_t base = ((uint32_t)px << 16) | (((pw[i][1] >> (r ? 1 : 8)) & 0x7Fu) * 32u);
+                while (m) {
+                  const int jb = __clz(m);
+                  m &= ~(0x80000000u >> jb);
+                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
+                  wa += 4;
+                }
+              }
             }
           }
         }
-      }
-      quad_bar(quad);                                     // (C) winners of single-candidate pixels and the work list are visible
-      TC_TICK(3);
-      const int nitems = min(wl_count[quad], TC_WLCAP);
-#ifdef VQ_TC_TIMING
-      tacc[7] += nitems;
-#endif
-      if (nitems > 0) {
-        // ---- exact fp32 re-rank of the listed (pixel, code) pairs ----------------------------------
-        // One warp of the quadrant (rotating), one lane per pair: the dot product is the same ascending-d fma
-        // chain as in the CUDA-core kernels (which reproduces the reference's fp32 GEMM for these sizes).
-        if (cg == (it & (TC_NCG - 1))) {
-          for (int i = lane; i < nitems; i += 32) {
+        const uint32_t fbm = __ballot_sync(0xffffffffu, fb && hf == 0);   // the partner lane learns about the overflow
+        fb = ((fbm >> px) & 1u) != 0;
+        // pairs are listed up to the first pixel that did not fit
+        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TC_WLCAP) ? pos : npairs);
+        __syncwarp();
+        unsigned long long key = 0ull;                    // my pair's (score, -original index, position)
+        for (int i0 = 0; i0 < nlist; i0 += 32) {
+          const int i = i0 + lane;
+          unsigned long long kcur = 0ull;
+          if (i < nlist) {
             uint32_t item;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
-            const int pp = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+            const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+            const int pp = ow * 16 + ppx;
             const int kb = k >> bnsh, row = k & (P.BN - 1);
             uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
             const uint32_t r7 = (uint32_t)(row & 7) << 4;
-            uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
+            const uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
             const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
             const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
             float dot = 0.f;
@@ -806,42 +848,41 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
             // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
             const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
             const float e2k = -2.f * ((au.z + au.y) + au.x);
-            const float sc = ref_score(dot, e2k, lds_f32(zn_s + (uint32_t)(s * TC_TILE + pp) * 8 + 4));
+            const float sc = ref_score(dot, e2k, lds_f32(zn_s + (uint32_t)(s * TC_TILE + pp) * 4));
             // ties go to the lowest ORIGINAL index
-            const unsigned long long key = ((unsigned long long)f32_orderable(sc) << 32) |
-                                           ((unsigned long long)(0xFFFFu - korig) << 16) | (unsigned long long)k;
-            atomicMax((unsigned long long*)(smem + P.off_best) + (it & 1) * TC_TILE + pp, key);
+            kcur = ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - korig) << 16) |
+                   (unsigned long long)k;
+          }
+          // every pixel lane picks the best of its pairs that were scored in this round (pairs of a pixel are contiguous)
+          const int rel = pos - i0;                       // my first pair, relative to this round
+          const int maxmine = __reduce_max_sync(0xffffffffu, mine);
+          for (int t = 0; t < maxmine; ++t) {
+            const int src = rel + t;
+            const bool take = t < mine && src >= 0 && src < 32;
+            const unsigned long long kk = __shfl_sync(0xffffffffu, kcur, take ? src : 0);
+            if (take && kk > key) key = kk;
           }
         }
-        TC_TICK(8);
-        quad_bar(quad);                                   // (D) all pairs of this quadrant are scored
-        if (cg == 0 && lane == 0) wl_count[quad] = 0;
-      }
-      TC_TICK(4);
-      int w = 0;
-      if (!fb) {
-        if (total == 1) {
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(win_s));
-        } else {
-          uint32_t klo, khi;
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(klo), "=r"(khi) : "r"(bestc + (uint32_t)p * 8));
-          if ((klo & khi) == 0xFFFFFFFFu || (klo | khi) == 0u) fb = true;
-          else w = (int)(klo & 0xFFFFu);
-        }
+        // hand the winner to the partner lane (hf == 1) of the pixel
+        const unsigned long long kp = __shfl_sync(0xffffffffu, key, px);
+        if (total > 1 && !fb) w = (int)(kp & 0xFFFFull);
       }
 
-      TC_TICK(10);
-      // ---- outputs: ids, q, (z-q)^2, EMA statistics (channel quads j == cg mod TC_NCG) ------------
+      TC_TICK(3);
+#ifdef VQ_TC_TIMING
+      tacc[7] += npairs;
+#endif
+      // ---- outputs: ids, q, (z-q)^2, EMA statistics ----------------------------------------------------
       const int pp = p0 + p;
       if (fb) {
-        if (cg == 0) {
+        if (hf == 0) {
           const int slot = atomicAdd(P.fb_count, 1);
           P.fb_rows[slot] = b * P.HW + pp;
         }
       } else {
         uint32_t worig;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(worig) : "r"(perm_a + (uint32_t)w * 2));
-        if (cg == 0) {
+        if (hf == 0) {
           int h, wc;
           if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
           else { h = pp / P.W; wc = pp - h * P.W; }
@@ -850,58 +891,51 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           if (P.ids_nat) P.ids_nat[nb_ + pp] = (int)worig;
           if (STATS) atomicAdd(&hist[worig], 1);
         }
-        TC_TICK(11);
         const int kb = w >> bnsh, row = w & (P.BN - 1);
         const uint32_t r7 = (uint32_t)(row & 7);
-        // two quads per 32-channel chunk for this thread (jj = cg and cg + 4); their shared-memory loads are issued
-        // together, before the first dependent instruction
-        uint32_t ea = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
-        const uint32_t za = zrow + (uint32_t)cg * 512;
-        const uint32_t eo0 = (((uint32_t)cg ^ r7) << 4), eo1 = ((((uint32_t)cg + 4) ^ r7) << 4);
-        float* qo = P.q + (size_t)b * img_stride + (size_t)(4 * cg) * hw + pp;
+        // channel quads j = 2t + hf: chunk j >> 3, quad-in-chunk j & 7
+        const uint32_t ea = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
+        float* qo = P.q + (size_t)b * img_stride + pp;
         float* so = STATS ? sums_mine + (size_t)worig * Dc : nullptr;
-        constexpr bool kFull = DT != 0 && DT % TC_DCH == 0;   // every chunk complete: no channel guards
+        auto quad_out = [&](int j) {
+          const int ci = j >> 3, jj = j & 7;
+          const float4 e4 = lds_v4(ea + (uint32_t)ci * bn128 + ((((uint32_t)jj) ^ r7) << 4));
+          const uint32_t zj = zrow + (uint32_t)ci * 16384 + (uint32_t)jj * 512;
+          float zv[4];
 #pragma unroll
-        for (int ci = 0; ci < nD; ++ci) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (kFull || ci * 32 + 4 * cg + 16 * t < Dc) {
-              const float4 e4 = lds_v4(ea + (t ? eo1 : eo0));
-              const uint32_t zj = za + (uint32_t)ci * 16384 + (uint32_t)t * 2048;
-              float zv[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) zv[i] = lds_f32(zj + zx[i]);
-              float df = zv[0] - e4.x; lsum = __fmaf_rn(df, df, lsum);
-              df = zv[1] - e4.y; lsum = __fmaf_rn(df, df, lsum);
-              df = zv[2] - e4.z; lsum = __fmaf_rn(df, df, lsum);
-              df = zv[3] - e4.w; lsum = __fmaf_rn(df, df, lsum);
-              float* qj = qo + (size_t)(32 * ci + 16 * t) * hw;
-              __stcs(qj, e4.x);
-              __stcs(qj + hw, e4.y);
-              __stcs(qj + 2 * hw, e4.z);
-              __stcs(qj + 3 * hw, e4.w);
-              if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 32 * ci + 16 * t), make_float4(zv[0], zv[1], zv[2], zv[3]));
-            }
+          for (int i = 0; i < 4; ++i) zv[i] = lds_f32(zj + zx[i]);
+          float df = zv[0] - e4.x; lsum = __fmaf_rn(df, df, lsum);
+          df = zv[1] - e4.y; lsum = __fmaf_rn(df, df, lsum);
+          df = zv[2] - e4.z; lsum = __fmaf_rn(df, df, lsum);
+          df = zv[3] - e4.w; lsum = __fmaf_rn(df, df, lsum);
+          if (!DBG || P.q) {
+            float* qj = qo + (size_t)(4 * j) * hw;
+            __stcs(qj, e4.x);
+            __stcs(qj + hw, e4.y);
+            __stcs(qj + 2 * hw, e4.z);
+            __stcs(qj + 3 * hw, e4.w);
           }
-          ea += bn128;
+          if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(zv[0], zv[1], zv[2], zv[3]));
+        };
+        if (DT != 0 && DT % 8 == 0) {
+#pragma unroll
+          for (int t = 0; t < DT / 8; ++t) quad_out(2 * t + hf);
+        } else {
+#pragma unroll 1
+          for (int j = hf; j < nq; j += 2) quad_out(j);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(3 + s));             // z stage free
-      TC_TICK(5);
     }
-#ifdef VQ_TC_TIMING
-    if (lane == 0 && blockIdx.x < 148) {
-      tacc[6] = my_tiles;
-      for (int i = 0; i < 16; ++i) g_tc_timing[((size_t)blockIdx.x * TC_EPI_WARPS + (warp - TC_AUX_WARPS)) * 16 + i] = tacc[i];
-    }
-#endif
+    TC_TICK(4);
+    TC_TIMING_STORE(8 + ow, my_tiles);
     // ---- per-CTA reductions ------------------------------------------------------------------
     lsum = warp_sum(lsum);
     if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
-    asm volatile("bar.sync 5, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");        // all epilogue warps
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_OUT_WARPS) : "memory");        // all output warps
     if (STATS) {
-      for (int k = threadIdx.x - 32 * TC_AUX_WARPS; k < P.K; k += 32 * TC_EPI_WARPS) {
+      for (int k = threadIdx.x - 32 * (TC_AUX_WARPS + TC_SCAN_WARPS); k < P.K; k += 32 * TC_OUT_WARPS) {
         const int c = hist[k];
         if (c) atomicAdd(&P.counts[k], c);
       }
@@ -949,7 +983,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
   const TcGeom g = tc_geometry(a.D, a.K);
   VQ_REQUIRE(g.ok && g.nb * g.BN <= TC_SORT_MAX && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
-  VQ_REQUIRE(a.q != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
+  VQ_REQUIRE(a.q != nullptr || dbg != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
   EncodeTiledFn enc = get_encode_fn();
   VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
@@ -996,8 +1030,8 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   P.tiles_per_img = HW / TC_TILE;
   P.ntiles = a.B * P.tiles_per_img;
   P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;
-  P.off_z = (uint32_t)g.off_z; P.off_pub = (uint32_t)g.off_pub; P.off_win = (uint32_t)g.off_win;
-  P.off_best = (uint32_t)g.off_best; P.off_wl = (uint32_t)g.off_wl; P.off_zn = (uint32_t)g.off_zn;
+  P.off_z = (uint32_t)g.off_z; P.off_pub = (uint32_t)g.off_pub;
+  P.off_wl = (uint32_t)g.off_wl; P.off_zn = (uint32_t)g.off_zn;
   P.off_hist = (uint32_t)g.off_hist; P.off_perm = (uint32_t)g.off_perm; P.off_ctab = (uint32_t)g.off_ctab;
   P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
@@ -1034,13 +1068,13 @@ int launch_assign_tc(const FwdArgs& a, cudaStream_t s) { return launch_assign_tc
 
 int tc_debug_timing(long long* host_out, int n) {
 #ifdef VQ_TC_TIMING
-  const int tot = 148 * TC_EPI_WARPS * 16;
+  const int tot = 148 * 16 * 8;
   if (n < tot) return -1;
   if (cudaMemcpyFromSymbol(host_out, g_tc_timing, sizeof(long long) * tot) != cudaSuccess) return -2;
   return tot;
 #else
   (void)host_out; (void)n;
-  return 0;
+  return 0;                      // role timing is not compiled into this build
 #endif
 }
 

@@ -33,19 +33,19 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 print("forward ms", e0.elapsed_time(e1))
-buf = np.zeros(148 * 16 * 16, dtype=np.int64)
+buf = np.zeros(148 * 16 * 8, dtype=np.int64)
 n = L.vq_debug_tc_timing(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
 print("timing entries", n)
 if n > 0:
-    t = buf.reshape(148, 16, 16).astype(np.float64)
+    t = buf.reshape(148, 16, 8).astype(np.float64)
     tiles = t[:, :, 6].mean()
-    names = ["wait z/zn", "scan", "merge(A)", "push(C)", "barrier D", "q/sums", "-", "-", "rerank work", "wait tmem", "decode", "ids/hist"]
-    tot = (t[:, :, :6].sum(axis=2) + t[:, :, 8:12].sum(axis=2)).mean()
-    print(f"re-rank pairs per quadrant and tile: mean {(t[:, :, 7] / t[:, :, 6]).mean():.2f} max {(t[:, :, 7] / t[:, :, 6]).max():.2f}")
-    print(f"tiles per CTA {tiles:.1f}; cycles per tile (mean over warps) {tot / tiles:.0f}")
-    for i, nm in enumerate(names):
-        if nm == '-':
-            continue
-        per = t[:, :, i] / t[:, :, 6]
-        print(f"  {nm:10s} mean {per.mean():8.0f}  min {per.min():8.0f}  max {per.max():8.0f}   by cg: " +
-              " ".join(f"{per.reshape(148, 4, 4)[:, c, :].mean():7.0f}" for c in range(4)))
+    print(f"tiles per CTA {tiles:.1f}")
+    for role, sl, names in (("scan warps", slice(0, 8), ["wait |z|^2", "wait tmem", "scan work", "wait pub slot", "publish+loop"]),
+                            ("output warps", slice(8, 16), ["wait z/|z|^2", "wait scan", "merge", "pairs+rerank", "outputs"])):
+        r = t[:, sl, :]
+        tot = r[:, :, :5].sum(axis=2).mean() / tiles
+        print(f"{role}: cycles per tile {tot:.0f}")
+        for i, nm in enumerate(names):
+            per = r[:, :, i] / r[:, :, 6]
+            print(f"  {nm:14s} mean {per.mean():8.0f}  min {per.min():8.0f}  max {per.max():8.0f}")
+    print(f"re-rank pairs per output warp and tile: {(t[:, 8:, 7] / t[:, 8:, 6]).mean():.2f}")
