@@ -151,6 +151,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float2 lds_v2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -441,7 +446,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
   if (threadIdx.x == 32) {
     mbar_init(BAR(0), 1);
     mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-    mbar_init(BAR(3), TC_OUT_WARPS + 2); mbar_init(BAR(4), TC_OUT_WARPS + 2);
+    mbar_init(BAR(3), TC_OUT_WARPS + 3); mbar_init(BAR(4), TC_OUT_WARPS + 3);   // output warps, |z|^2 warps, MMA commit
     mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
     mbar_init(BAR(7), TC_SCAN_WARPS); mbar_init(BAR(8), TC_SCAN_WARPS);
     mbar_init(BAR(9), 2); mbar_init(BAR(10), 2);
@@ -531,12 +536,14 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           }
           umma_commit(BAR(5 + a));
         }
+        umma_commit(BAR(3 + s));               // the tensor core is done reading this z stage
       }
     }
   } else if (warp < TC_AUX_WARPS) {
     // ===================================== |z|^2 workers ====================================
-    // two warps, two pixels per lane; same ascending-d fma chain as the CUDA-core kernels
-    const int pA = (warp - 2) * 64 + lane;                // second pixel: pA + 32 (same swizzle phase)
+    // two warps, two ADJACENT pixels per lane (one 8-byte shared-memory load, one packed fma per channel); per
+    // pixel this is the same ascending-d fma chain as in the CUDA-core kernels
+    const int pA = (warp - 2) * 64 + 2 * lane;            // pixels pA, pA + 1 (same 16-byte atom)
     const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
     const uint32_t zn_s = sbase + P.off_zn;
     uint32_t zx[4];
@@ -546,22 +553,20 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const int s = two_stages ? (it & 1) : 0, ph = two_stages ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(BAR(1 + s), ph);
       uint32_t zc = zrow0 + s * zstage_bytes;
-      float za = 0.f, zb = 0.f;
+      float2 zz = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < nD; ++c) {                      // channels beyond D are zero-filled by TMA: no guards
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float va = lds_f32(zc + jj * 512 + zx[i]), vb = lds_f32(zc + jj * 512 + 4096 + zx[i]);
-            za = __fmaf_rn(va, va, za);
-            zb = __fmaf_rn(vb, vb, zb);
+            const float2 v = lds_v2(zc + jj * 512 + zx[i]);
+            zz = __ffma2_rn(v, v, zz);
           }
         }
         zc += 16384;
       }
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(zn_s + (uint32_t)(s * TC_TILE + pA) * 4), "f"(za) : "memory");
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(zn_s + (uint32_t)(s * TC_TILE + pA + 32) * 4), "f"(zb) : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(zn_s + (uint32_t)(s * TC_TILE + pA) * 4), "f"(zz.x), "f"(zz.y) : "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(BAR(9 + s)); mbar_arrive(BAR(3 + s)); }
     }
@@ -626,12 +631,17 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           L = fmaxf(L, cm - delta);
           if (Urec < L) { cnt = 0; Urec = -INFINITY; }    // nothing recorded so far can still win
           const float T = L - delta;
+          const float2 nT2 = make_float2(-T, -T);
           uint32_t n4[4];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {                   // four independent sign-bit chains
             uint32_t nm = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nm = __funnelshift_l(__float_as_uint(v[8 * h + j] - T), nm, 1);
+            for (int j = 0; j < 8; j += 2) {
+              const float2 d2 = __fadd2_rn(make_float2(v[8 * h + j], v[8 * h + j + 1]), nT2);
+              nm = __funnelshift_l(__float_as_uint(d2.x), nm, 1);
+              nm = __funnelshift_l(__float_as_uint(d2.y), nm, 1);
+            }
             n4[h] = nm;
           }
           const uint32_t nmall = (n4[0] << 24) | (n4[1] << 16) | (n4[2] << 8) | n4[3];
@@ -682,6 +692,10 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     // pixel are taken inside one warp.  Per tile: merge the scan warps' bounds -> single candidate or a list of
     // (pixel, code) pairs -> exact fp32 re-rank of the pairs (one lane per pair, ascending-d fma chain) -> ids, q,
     // (z-q)^2, EMA statistics for the channel quads j == hf (mod 2).
+    // ZREG (emb_dim known at compile time, <= 64): the thread keeps its 4*NZQ z values in registers, so the z stage
+    // goes back to the TMA producer before the scan results even arrive; the re-rank reads z through shuffles.
+    constexpr bool ZREG = DT != 0 && DT % 8 == 0 && DT <= 64;
+    constexpr int NZQ = ZREG ? DT / 8 : 1;                // channel quads per thread
     const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
     const int px = lane & 15, hf = lane >> 4;
     const int p = ow * 16 + px;                           // pixel within the tile
@@ -706,7 +720,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     }
     const size_t hw = (size_t)P.HW;
     const size_t img_stride = (size_t)Dc * hw;
-    float lsum = 0.f;
+    float2 ls2 = make_float2(0.f, 0.f);                   // two partial sums of (z-q)^2
     int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile -> (image, tile in image)
     mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
     TC_TIMING_DECL
@@ -720,12 +734,28 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const uint32_t zrow = zrow0 + zst;
       TC_TICK(4);
       mbar_wait(BAR(1 + s), ph);                          // z tile (TMA writes) visible to this thread
+      float zq[NZQ][4];                                   // ZREG: z of channels 4*(2t+hf)+i
+      if (ZREG) {
+#pragma unroll
+        for (int t = 0; t < NZQ; ++t) {
+          const int j = 2 * t + hf;                       // hf is not a compile-time constant: address arithmetic
+          const uint32_t zj = zrow + (uint32_t)(t >> 2) * 16384 + (uint32_t)((2 * t) & 7) * 512 + (uint32_t)hf * 512;
+          (void)j;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) zq[t][i] = lds_f32(zj + zx[i]);
+        }
+      }
       mbar_wait(BAR(9 + s), ph);                          // |z|^2
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 4));
+      // ZREG: the |z|^2 of the pixels this warp may re-rank (lane l keeps pixel l & 15), then the stage is free
+      if (ZREG) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(3 + s));
+      }
       TC_TICK(0);
       mbar_wait(BAR(11 + par), pph);                      // scan results of this tile
       TC_TICK(1);
-      float z2;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)(s * TC_TILE + p) * 4));
       const float zn = sqrtf(z2) * 1.00001f;
       const bool bad = !(z2 <= 3.0e38f);
 
@@ -803,22 +833,37 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         // pairs are listed up to the first pixel that did not fit
         const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TC_WLCAP) ? pos : npairs);
         __syncwarp();
-        unsigned long long key = 0ull;                    // my pair's (score, -original index, position)
+        unsigned long long key = 0ull;                    // best (score, -original index, position) of my pixel's pairs
         for (int i0 = 0; i0 < nlist; i0 += 32) {
           const int i = i0 + lane;
-          unsigned long long kcur = 0ull;
-          if (i < nlist) {
-            uint32_t item;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
-            const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-            const int pp = ow * 16 + ppx;
-            const int kb = k >> bnsh, row = k & (P.BN - 1);
-            uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
-            const uint32_t r7 = (uint32_t)(row & 7) << 4;
+          const bool act = i < nlist;
+          uint32_t item = 0;                              // idle lanes score (pixel 0, code 0) and drop the result
+          if (act) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
+          const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+          const int pp = ow * 16 + ppx;
+          const int kb = k >> bnsh, row = k & (P.BN - 1);
+          uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
+          const uint32_t r7 = (uint32_t)(row & 7) << 4;
+          float dot = 0.f;
+          if (ZREG) {
+            // z(pixel ppx, channel 4j+i) lives in lane ppx + 16*(j&1), register zq[j>>1][i]
+#pragma unroll
+            for (int j = 0; j < 2 * NZQ; ++j) {
+              const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) << 4) ^ r7));
+              const int src = ppx + 16 * (j & 1);
+              const float z0 = __shfl_sync(0xffffffffu, zq[j >> 1][0], src);
+              const float z1 = __shfl_sync(0xffffffffu, zq[j >> 1][1], src);
+              const float z2s = __shfl_sync(0xffffffffu, zq[j >> 1][2], src);
+              const float z3 = __shfl_sync(0xffffffffu, zq[j >> 1][3], src);
+              dot = __fmaf_rn(z0, e4.x, dot);
+              dot = __fmaf_rn(z1, e4.y, dot);
+              dot = __fmaf_rn(z2s, e4.z, dot);
+              dot = __fmaf_rn(z3, e4.w, dot);
+            }
+          } else {
             const uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
             const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
             const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
-            float dot = 0.f;
 #pragma unroll
             for (int c = 0; c < nD; ++c) {                  // zero-padded chunks: no guards
 #pragma unroll
@@ -843,16 +888,17 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
               }
               eb += bn128;
             }
-            uint32_t korig;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
-            // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
-            const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
-            const float e2k = -2.f * ((au.z + au.y) + au.x);
-            const float sc = ref_score(dot, e2k, lds_f32(zn_s + (uint32_t)(s * TC_TILE + pp) * 4));
-            // ties go to the lowest ORIGINAL index
-            kcur = ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - korig) << 16) |
-                   (unsigned long long)k;
           }
+          uint32_t korig;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
+          // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
+          const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
+          const float e2k = -2.f * ((au.z + au.y) + au.x);
+          const float z2p = __shfl_sync(0xffffffffu, z2, ppx);           // lane ppx holds |z|^2 of pixel ppx
+          const float sc = ref_score(dot, e2k, z2p);
+          // ties go to the lowest ORIGINAL index
+          const unsigned long long kcur = !act ? 0ull :
+              ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - korig) << 16) | (unsigned long long)k;
           // every pixel lane picks the best of its pairs that were scored in this round (pairs of a pixel are contiguous)
           const int rel = pos - i0;                       // my first pair, relative to this round
           const int maxmine = __reduce_max_sync(0xffffffffu, mine);
@@ -897,17 +943,13 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         const uint32_t ea = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
         float* qo = P.q + (size_t)b * img_stride + pp;
         float* so = STATS ? sums_mine + (size_t)worig * Dc : nullptr;
-        auto quad_out = [&](int j) {
-          const int ci = j >> 3, jj = j & 7;
-          const float4 e4 = lds_v4(ea + (uint32_t)ci * bn128 + ((((uint32_t)jj) ^ r7) << 4));
-          const uint32_t zj = zrow + (uint32_t)ci * 16384 + (uint32_t)jj * 512;
-          float zv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) zv[i] = lds_f32(zj + zx[i]);
-          float df = zv[0] - e4.x; lsum = __fmaf_rn(df, df, lsum);
-          df = zv[1] - e4.y; lsum = __fmaf_rn(df, df, lsum);
-          df = zv[2] - e4.z; lsum = __fmaf_rn(df, df, lsum);
-          df = zv[3] - e4.w; lsum = __fmaf_rn(df, df, lsum);
+        auto quad_out = [&](int j, float z0, float z1, float z2v, float z3) {
+          const float4 e4 = lds_v4(ea + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) ^ r7) << 4));
+          const float2 m1 = make_float2(-1.f, -1.f);      // z - e as one packed fma (exact: e * -1 + z)
+          const float2 d01 = __ffma2_rn(make_float2(e4.x, e4.y), m1, make_float2(z0, z1));
+          const float2 d23 = __ffma2_rn(make_float2(e4.z, e4.w), m1, make_float2(z2v, z3));
+          ls2 = __ffma2_rn(d01, d01, ls2);
+          ls2 = __ffma2_rn(d23, d23, ls2);
           if (!DBG || P.q) {
             float* qj = qo + (size_t)(4 * j) * hw;
             __stcs(qj, e4.x);
@@ -915,21 +957,27 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
             __stcs(qj + 2 * hw, e4.z);
             __stcs(qj + 3 * hw, e4.w);
           }
-          if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(zv[0], zv[1], zv[2], zv[3]));
+          if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
         };
-        if (DT != 0 && DT % 8 == 0) {
+        if (ZREG) {
 #pragma unroll
-          for (int t = 0; t < DT / 8; ++t) quad_out(2 * t + hf);
+          for (int t = 0; t < NZQ; ++t) quad_out(2 * t + hf, zq[t][0], zq[t][1], zq[t][2], zq[t][3]);
         } else {
 #pragma unroll 1
-          for (int j = hf; j < nq; j += 2) quad_out(j);
+          for (int j = hf; j < nq; j += 2) {
+            const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+            quad_out(j, lds_f32(zj + zx[0]), lds_f32(zj + zx[1]), lds_f32(zj + zx[2]), lds_f32(zj + zx[3]));
+          }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(3 + s));             // z stage free
+      if (!ZREG) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(3 + s));           // z stage free
+      }
     }
     TC_TICK(4);
     TC_TIMING_STORE(8 + ow, my_tiles);
+    float lsum = ls2.x + ls2.y;
     // ---- per-CTA reductions ------------------------------------------------------------------
     lsum = warp_sum(lsum);
     if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
