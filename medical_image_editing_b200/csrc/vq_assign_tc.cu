@@ -41,7 +41,7 @@ constexpr int TC_AUX_WARPS = 4;     // TMA producer, MMA issuer, two |z|^2 worke
 constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_SCAN_WARPS + TC_OUT_WARPS);
 constexpr int TC_WLCAP = 32;        // (pixel, code) pairs re-scored exactly per output warp and tile
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_SORT_MAX = 4096;     // codes the single-CTA sort of vq_tc_prep2_kernel handles
+constexpr int TC_SORT_MAX = 4096;     // codes (16-bit sorted positions, 7-bit chunk indices in the epilogue)
 constexpr int TC_MAX_REP = 32;        // replicas of the per-code sums (spreads the L2 reduction traffic)
 
 struct TcGeom {
@@ -120,15 +120,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires),
+  // so a waiting warp does not burn issue slots of its SM sub-partition
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
 // polling wait with nanosleep back-off: used by the single-thread producer / MMA roles so that their spinning
@@ -242,115 +244,89 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 // one bound per chunk (largest norm in the chunk).  Codes whose norm exceeds 64x the lower edge of the median
 // exponent bin ("big": the exploded dead codes of EMA training) are excluded from the
 // approximate search (augmentation = -1e30) and handled by a rigorous per-row test in the main kernel.
-//   ctab[c] = (A_c, B_c):  bound_c(|z|) = |z| * A_c + B_c        (accumulator units)
-//   meta[1] = r_minbig (smallest norm of an excluded code, rounded down; +inf if none)
-__global__ void __launch_bounds__(1024)
+//   rmax[c]  = largest live norm in sorted chunk c (uint32 bits of a non-negative float; zeroed by vq_prep_kernel);
+//              the main kernel turns it into bound_c(|z|) = |z| * A_c + B_c  (accumulator units)
+//   meta[0] = r_cap, meta[1] = smallest norm of an excluded code as uint32 bits (0x7F800000 = none; set by prep)
+//
+// Rank by counting: every thread owns one sorted-order key (norm bits, original index) and counts the smaller keys
+// in shared memory -- O(K^2 / threads) compares, no sorting network, any number of CTAs.
+constexpr int TC_PREP2_THREADS = 256;
+__global__ void __launch_bounds__(TC_PREP2_THREADS)
 vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, int K, int D, int BN, int nb,
                    float* __restrict__ es, float* __restrict__ eaug_img, int* __restrict__ perm,
-                   float* __restrict__ ctab, float* __restrict__ meta) {
-  __shared__ unsigned long long keys[TC_SORT_MAX];
+                   uint32_t* __restrict__ rmax, uint32_t* __restrict__ meta) {
+  extern __shared__ uint32_t keys[];          // [K] norm bits (NaN / negative -> +inf)
   __shared__ int hist[256];
   __shared__ float s_rcap;
-  __shared__ float red_min[32];
   const int tid = threadIdx.x;
   const int ktot = nb * BN;
-  int npow = 1;
-  while (npow < ktot) npow <<= 1;
-  if (tid < 256) hist[tid] = 0;
+  hist[tid] = 0;                              // TC_PREP2_THREADS == 256
   __syncthreads();
-  for (int k = tid; k < npow; k += blockDim.x) {
-    unsigned long long key = ~0ull;                             // padding sorts last
-    if (k < K) {
-      const float r = sqrtf(e2[k]);
-      atomicAdd(&hist[(__float_as_uint(r) >> 23) & 0xFF], 1);
-      uint32_t rb = __float_as_uint(r);
-      if (!(r >= 0.f)) rb = 0x7F800000u;                        // NaN norms sort with +inf
-      key = ((unsigned long long)rb << 32) | (uint32_t)k;
-    }
-    keys[k] = key;
+  for (int k = tid; k < K; k += blockDim.x) {
+    const float r = sqrtf(e2[k]);
+    uint32_t rb = __float_as_uint(r);
+    if (!(r >= 0.f)) rb = 0x7F800000u;
+    keys[k] = rb;
+    atomicAdd(&hist[(rb >> 23) & 0xFF], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int cum = 0, emed = 0;
-    for (int e = 0; e < 256; ++e) { cum += hist[e]; if (2 * cum >= K) { emed = e; break; } }
-    int ecap = emed + 6;                                        // 64 x the lower edge of the median exponent bin
-    if (ecap > 254) ecap = 254;
-    s_rcap = __uint_as_float((uint32_t)ecap << 23);
-  }
-  // bitonic sort, ascending (norm, original index)
-  for (int size = 2; size <= npow; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int i = tid; i < npow; i += blockDim.x) {
-        const int j = i ^ stride;
-        if (j > i) {
-          const unsigned long long a = keys[i], b = keys[j];
-          const bool up = (i & size) == 0;
-          if ((a > b) == up) { keys[i] = b; keys[j] = a; }
-        }
+  if (tid < 32) {                             // median exponent bin: warp-parallel prefix over the 256 bins
+    int cum = 0, emed = 255;
+    bool found = false;
+    for (int base = 0; base < 256 && !found; base += 32) {
+      int v = hist[base + tid];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (tid >= o) v += t;
       }
+      const uint32_t hit = __ballot_sync(0xffffffffu, 2 * (cum + v) >= K);
+      if (hit) { emed = base + __ffs(hit) - 1; found = true; }
+      cum += __shfl_sync(0xffffffffu, v, 31);
     }
+    int ecap = emed + 6;                      // 64 x the lower edge of the median exponent bin
+    if (ecap > 254) ecap = 254;
+    if (tid == 0) s_rcap = __uint_as_float((uint32_t)ecap << 23);
   }
   __syncthreads();
   const float rcap = s_rcap;
-  const float c1 = 0.00390625f * 1.03f;                         // 2^-8: z and e both truncated to tf32 (score units)
-  const float c2 = (float)(D + 16) * 4.76837158e-7f;            // (D+16) 2^-21: fp32 accumulation in the tensor core
   const float slop = 1.f + (float)D * 1.2e-7f + 1e-5f;          // |e| was computed in fp32 from a rounded |e|^2
-  // per sorted position: perm, augmentation image
-  float rb = INFINITY;
-  for (int i = tid; i < ktot; i += blockDim.x) {
-    const unsigned long long key = keys[i];
-    const int k = (int)(uint32_t)key;
-    const float r = __uint_as_float((uint32_t)(key >> 32));
-    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;                      // padding / excluded codes never win
-    const bool real = key != ~0ull;
-    perm[i] = real ? k : 0;
+  const int i = blockIdx.x * blockDim.x + tid;                 // code (i < K) or padding slot (K <= i < ktot)
+  if (i == 0) meta[0] = __float_as_uint(rcap);
+  if (i < ktot) {
+    int pos = i;                              // padding keeps its slot: K .. ktot-1
+    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;    // padding / excluded codes never win
+    const bool real = i < K;
     if (real) {
+      const uint32_t mine = keys[i];
+      int rank = 0;
+      for (int j = 0; j < K; ++j) {           // broadcast reads
+        const uint32_t kj = keys[j];
+        rank += (kj < mine || (kj == mine && j < i)) ? 1 : 0;
+      }
+      pos = rank;
+      const float r = __uint_as_float(mine);
       if (r <= rcap) {
-        const float x = -0.5f * e2[k];
+        const float x = -0.5f * e2[i];
         a0 = tf32_trunc(x);
         const float r1 = x - a0;
         a1 = tf32_trunc(r1);
         a2 = tf32_trunc(r1 - a1);
+        atomicMax(&rmax[pos >> 5], __float_as_uint(r * slop));
       } else {
-        rb = fminf(rb, r);
+        atomicMin(&meta[1], __float_as_uint(r / slop));
       }
     }
-    const int blk = i / BN, rr = i % BN, grp = rr >> 3, row = rr & 7;
+    perm[pos] = real ? i : 0;
+    const int blk = pos / BN, rr = pos % BN, grp = rr >> 3, row = rr & 7;
     float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
     base[0] = a0; base[1] = a1; base[2] = a2; base[3] = 0.f;
     base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
-  }
-  // per 32-code chunk: largest live norm -> bound coefficients (accumulator units = score units / 2)
-  for (int c = tid; c < ktot / 32; c += blockDim.x) {
-    float rmax = 0.f;
-    for (int i = c * 32; i < c * 32 + 32; ++i) {
-      const unsigned long long key = keys[i];
-      if (key != ~0ull) {
-        const float r = __uint_as_float((uint32_t)(key >> 32));
-        if (r <= rcap) rmax = fmaxf(rmax, r);
-      }
-    }
-    rmax *= slop;
-    ctab[2 * c] = 0.5f * (c1 + c2) * rmax;                      // A_c
-    ctab[2 * c + 1] = 0.5f * c2 * rmax * rmax + 1e-30f;         // B_c
-  }
-  for (int o = 16; o > 0; o >>= 1) rb = fminf(rb, __shfl_xor_sync(0xffffffffu, rb, o));
-  if ((tid & 31) == 0) red_min[tid >> 5] = rb;
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) rb = fminf(rb, red_min[i]);
-    meta[0] = rcap;
-    meta[1] = rb / slop;
-  }
-  // sorted copy of the codebook rows (TMA source)
-  const int dq = D >> 2;
-  for (int i = tid; i < ktot * dq; i += blockDim.x) {
-    const int pos = i / dq, j = i - pos * dq;
-    const unsigned long long key = keys[pos];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (key != ~0ull) v = __ldg(reinterpret_cast<const float4*>(E + (size_t)(uint32_t)key * D) + j);
-    reinterpret_cast<float4*>(es + (size_t)pos * D)[j] = v;
+    // sorted copy of the codebook row (TMA source)
+    const int dq = D >> 2;
+    float4* dst = reinterpret_cast<float4*>(es + (size_t)pos * D);
+    const float4* src = reinterpret_cast<const float4*>(E + (size_t)(real ? i : 0) * D);
+    for (int j = 0; j < dq; ++j) dst[j] = real ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -358,8 +334,8 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
 // main kernel
 // ---------------------------------------------------------------------------------------------
 struct TcParams {
-  const float* z; const float* E; const float* e2; const float* eaug_img; const float* meta;
-  const int* perm; const float* ctab;
+  const float* z; const float* E; const float* e2; const float* eaug_img; const uint32_t* meta;
+  const int* perm; const uint32_t* rmax;
   int B, D, H, W, HW, K;
   int BN, nb, nD, nst;
   int bn_shift;           // BN == 1 << bn_shift
@@ -470,7 +446,15 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     }
     for (int k = t; k < P.K; k += NT) hist[k] = 0;
     for (int k = t; k < ktot; k += NT) perm_s[k] = (uint16_t)P.perm[k];
-    for (int c = t; c < 2 * P.nb * (P.BN >> 5); c += NT) ((float*)(smem + P.off_ctab))[c] = P.ctab[c];
+    {   // per-chunk error-bound coefficients from the chunk's largest norm (already includes the rounding slop)
+      const float c1 = 0.00390625f * 1.03f;                     // 2^-8: z and e both truncated to tf32 (score units)
+      const float c2 = (float)(Dc + 16) * 4.76837158e-7f;       // (D+16) 2^-21: fp32 accumulation in the tensor core
+      for (int c = t; c < P.nb * (P.BN >> 5); c += NT) {
+        const float rm = __uint_as_float(P.rmax[c]);
+        ((float*)(smem + P.off_ctab))[2 * c] = 0.5f * (c1 + c2) * rm;                 // A_c
+        ((float*)(smem + P.off_ctab))[2 * c + 1] = 0.5f * c2 * rm * rm + 1e-30f;      // B_c
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -699,7 +683,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
     const int px = lane & 15, hf = lane >> 4;
     const int p = ow * 16 + px;                           // pixel within the tile
-    const float rminbig = P.meta[1];
+    const float rminbig = __uint_as_float(P.meta[1]);   // +inf when no code is excluded
     const int bnsh = P.bn_shift;                          // BN == 1 << bnsh
     const uint32_t bn128 = (uint32_t)P.BN * 128;
     const int nq = Dc >> 2;
@@ -1060,15 +1044,17 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   }
 
   float* eaug_img = a.ws.tc_aug;
-  float* meta = a.ws.tc_meta;
-  vq_tc_prep2_kernel<<<1, 1024, 0, s>>>(a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm,
-                                        a.ws.tc_ctab, meta);
+  uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
+  uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
+  const int ktot = g.nb * g.BN;
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+      a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
 
   TcParams P{};
   P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
-  P.perm = a.ws.tc_perm; P.ctab = a.ws.tc_ctab;
+  P.perm = a.ws.tc_perm; P.rmax = rmax;
   P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
   P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nst = g.nst;
   P.bn_shift = 0;

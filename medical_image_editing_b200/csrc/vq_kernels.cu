@@ -88,7 +88,8 @@ int profile_read(double* total_ms, int* launches) {
 __global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kpad,
                                float* __restrict__ e2, float* __restrict__ et, float* __restrict__ snap,
                                float* __restrict__ stats, size_t stats_n, float* __restrict__ sums_rep, size_t rep_n,
-                               int* __restrict__ counts, double* __restrict__ loss_acc, int* __restrict__ misc) {
+                               int* __restrict__ counts, double* __restrict__ loss_acc, int* __restrict__ misc,
+                               uint32_t* __restrict__ tc_rmax, uint32_t* __restrict__ tc_meta) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nth = (size_t)gridDim.x * blockDim.x;
   // |e_k|^2 : one thread per code, ascending d, fused multiply-add chain
@@ -119,11 +120,15 @@ __global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kp
   for (size_t i = tid; i < (size_t)K; i += nth) counts[i] = 0;
   if (tid == 0) *loss_acc = 0.0;
   if (tid < 8) misc[tid] = 0;
+  // tensor-core path: per-chunk largest norm (atomicMax target) and the smallest excluded norm (atomicMin target)
+  for (size_t i = tid; i < (size_t)Kpad / 32; i += nth) tc_rmax[i] = 0u;
+  if (tid < 16) tc_meta[tid] = 0x7F800000u;
 }
 
 // =============================================================================================
 // exact fp32 search
 // =============================================================================================
+constexpr int FB_ROWS_MAX = 8192; // longer fallback lists go to the tiled search
 constexpr int SIMT_TP = 128;   // pixels per tile
 constexpr int SIMT_TK = 64;    // codes per pass
 constexpr int SIMT_DC = 32;    // channel chunk
@@ -153,6 +158,7 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
   int nrows = 0;
   if (list_mode) {
     nrows = *fb_count;
+    if (nrows <= FB_ROWS_MAX) return;               // short lists were handled by vq_fallback_rows_kernel
     ntiles = (nrows + SIMT_TP - 1) / SIMT_TP;
   } else {
     ntiles = (long long)B * ((HW + SIMT_TP - 1) / SIMT_TP);
@@ -316,50 +322,56 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
 }
 
 // =============================================================================================
-// exhaustive exact search for the few rows the tensor-core kernel could not decide: one warp per row,
-// codes spread over lanes (coalesced reads of the transposed codebook), same fma chains as above
+// exhaustive exact search for the few rows the tensor-core kernel could not decide: one CTA per row, codes
+// spread over the threads (coalesced reads of the transposed codebook), same fma chains as above.  Lists longer
+// than FB_ROWS_MAX are left to the tiled search (vq_assign_simt_kernel in list mode), which is launched right after.
 // =============================================================================================
-constexpr int FB_WARPS = 4;
-__global__ void __launch_bounds__(FB_WARPS * 32)
+constexpr int FB_THREADS = 256;
+__global__ void __launch_bounds__(FB_THREADS)
 vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ et, const float* __restrict__ e2,
                         const float* __restrict__ E, int D, int H, int W, int K, int Kpad,
                         const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
                         int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat, float* __restrict__ q,
                         double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums) {
-  extern __shared__ float zrow_all[];                 // [FB_WARPS][D]
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* zr = zrow_all + (size_t)wib * D;
+  extern __shared__ float zr[];                       // [D]
+  __shared__ float red_s[FB_THREADS / 32];
+  __shared__ int red_i[FB_THREADS / 32];
+  __shared__ int s_best;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const int nrows = *fb_count;
+  if (nrows > FB_ROWS_MAX) return;                    // the tiled list search handles long lists
   const int HW = H * W;
-  const int gw = blockIdx.x * FB_WARPS + wib, nw = gridDim.x * FB_WARPS;
   float lsum = 0.f;
-  for (int r = gw; r < nrows; r += nw) {
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
     const long long n = fb_rows[r];
     const long long b = n / HW, p = n - b * HW;
     const long long off = b * (long long)D * HW + p;
-    __syncwarp();
-    for (int d = lane; d < D; d += 32) zr[d] = __ldg(z + off + (long long)d * HW);
-    __syncwarp();
+    __syncthreads();
+    for (int d = tid; d < D; d += FB_THREADS) zr[d] = __ldg(z + off + (long long)d * HW);
+    __syncthreads();
     float z2 = 0.f;
     for (int d = 0; d < D; ++d) z2 = __fmaf_rn(zr[d], zr[d], z2);
     float best = -INFINITY;
     int bi = 0;
-    for (int k0 = 0; k0 < Kpad; k0 += 256) {           // 8 codes per lane in flight: lane, lane+32, ..., lane+224
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      const float* ep = et + k0 + lane;
-#pragma unroll 2
+    for (int k0 = 0; k0 < Kpad; k0 += 2 * FB_THREADS) {     // two codes per thread in flight: k, k + 256
+      const bool two = k0 + FB_THREADS < Kpad;
+      float acc0 = 0.f, acc1 = 0.f;
+      const float* ep = et + k0 + tid;
+#pragma unroll 8
       for (int d = 0; d < D; ++d) {
         const float zv = zr[d];
         const float* row = ep + (size_t)d * Kpad;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(zv, __ldg(row + 32 * i), acc[i]);
+        acc0 = __fmaf_rn(zv, __ldg(row), acc0);
+        if (two) acc1 = __fmaf_rn(zv, __ldg(row + FB_THREADS), acc1);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                    // ascending k per lane, strict '>' keeps the lowest index
-        const int k = k0 + lane + 32 * i;
-        const float sc = ref_score(acc[i], __ldg(e2 + k), z2);
+      {                                                      // ascending k per thread, strict '>' keeps the lowest index
+        const int k = k0 + tid;
+        const float sc = ref_score(acc0, __ldg(e2 + k), z2);
+        if (sc > best) { best = sc; bi = k; }
+      }
+      if (two) {
+        const int k = k0 + tid + FB_THREADS;
+        const float sc = ref_score(acc1, __ldg(e2 + k), z2);
         if (sc > best) { best = sc; bi = k; }
       }
     }
@@ -369,14 +381,24 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (!(best > -INFINITY)) bi = 0;                   // all-NaN row: the reference's topk returns index 0
-    if (lane == 0) {
+    if (lane == 0) { red_s[wib] = best; red_i[wib] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w2 = 1; w2 < FB_THREADS / 32; ++w2) {
+        const float ob = red_s[w2];
+        const int oi = red_i[w2];
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (!(best > -INFINITY)) bi = 0;                 // all-NaN row: the reference's topk returns index 0
+      s_best = bi;
       const int h = (int)(p / W), w = (int)(p % W);
       if (ids) ids[b * HW + (long long)w * H + h] = bi;
       if (ids_nat) ids_nat[n] = bi;
       if (counts) atomicAdd(&counts[bi], 1);
     }
-    for (int d = lane; d < D; d += 32) {
+    __syncthreads();
+    bi = s_best;
+    for (int d = tid; d < D; d += FB_THREADS) {
       const float ev = __ldg(E + (size_t)bi * D + d);
       const float df = zr[d] - ev;
       lsum = __fmaf_rn(df, df, lsum);
@@ -635,7 +657,8 @@ int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s) {
   const size_t rep_n = (a.stats && tc_path) ? (size_t)(tc_sums_replicas(a.K, a.D) - 1) * a.K * a.D : 0;
   if (rep_n > 0 && blocks < 2 * sm_count()) blocks = 2 * sm_count();
   vq_prep_kernel<<<blocks, 256, 0, s>>>(a.embed, a.K, a.D, Kpad, a.ws.e2, a.ws.et, a.snapshot, a.stats, stats_n,
-                                        a.ws.sums_rep, rep_n, a.ws.counts, a.ws.loss_acc, a.ws.misc);
+                                        a.ws.sums_rep, rep_n, a.ws.counts, a.ws.loss_acc, a.ws.misc,
+                                        reinterpret_cast<uint32_t*>(a.ws.tc_ctab), reinterpret_cast<uint32_t*>(a.ws.tc_meta));
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;
@@ -667,10 +690,17 @@ int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s
 int launch_fallback_rows(const FwdArgs& a, cudaStream_t s) {
   const int Kpad = pad_codes(a.K);
   float* sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
-  const size_t smem = (size_t)FB_WARPS * a.D * sizeof(float);
-  vq_fallback_rows_kernel<<<2 * sm_count(), FB_WARPS * 32, smem, s>>>(
+  const size_t smem = (size_t)a.D * sizeof(float);
+  // short lists: one CTA per row (latency-bound, finishes in a few microseconds) ...
+  vq_fallback_rows_kernel<<<4 * sm_count(), FB_THREADS, smem, s>>>(
       a.z, a.ws.et, a.ws.e2, a.embed, a.D, a.H, a.W, a.K, Kpad, a.ws.fb_rows, a.ws.misc, a.ids, a.ids_nat, a.q,
       a.ws.loss_acc, a.stats ? a.ws.counts : nullptr, sums);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  // ... long lists (degenerate codebooks): the tiled fp32 search over the listed rows; exits at once otherwise
+  vq_assign_simt_kernel<<<2 * sm_count(), 256, 0, s>>>(a.z, a.ws.et, a.ws.e2, a.embed, a.B, a.D, a.H, a.W, a.K, Kpad,
+                                                      a.ws.fb_rows, a.ws.misc, a.ids, a.ids_nat, a.q, a.ws.loss_acc,
+                                                      a.stats ? a.ws.counts : nullptr, sums);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;
