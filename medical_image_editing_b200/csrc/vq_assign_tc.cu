@@ -95,6 +95,8 @@ int tc_sums_replicas(int K, int D) {
   return (int)r;
 }
 
+static bool tcs_supported(int D, int K);
+
 bool tc_path_supported(int B, int D, int H, int W, int K) {
   const long long HW = (long long)H * W;
   if (B <= 0 || HW <= 0) return false;
@@ -102,7 +104,8 @@ bool tc_path_supported(int B, int D, int H, int W, int K) {
   if (D % 4 != 0 || D < 4) return false;        // 16-byte rows for TMA / float4 gathers
   if (K < 1) return false;
   const TcGeom g = tc_geometry(D, K);
-  return g.ok && g.nb * g.BN <= TC_SORT_MAX;
+  if (g.ok && g.nb * g.BN <= TC_SORT_MAX) return true;      // codebook resident in shared memory
+  return tcs_supported(D, K);                                // codebook streamed through shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -982,6 +985,541 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// streaming variant: codebooks that do not fit in shared memory (K*D*4 > ~140 KB, e.g. K=512 x D=256, K=4096 x D=64)
+// ---------------------------------------------------------------------------------------------
+// The z tile (128 pixels x D) stays resident as a ring of 32-channel chunks; the norm-sorted codebook streams through
+// a ring of [BN codes x 32 channels] stages (classic K-loop pipelining, one tcgen05.commit per stage).  Scan and merge
+// are the same as in the resident kernel; the output warps read the exact fp32 code rows from global memory (L2) and
+// hand the z chunks back to the producer one by one, so the next tile's z streams in while this tile is written out.
+struct TcsGeom {
+  int BN, nb, nD, nes;
+  size_t off_z, off_e, off_aug, off_aaug, off_pub, off_wl, off_zn, off_ctab, off_bar, total;
+  bool ok;
+};
+constexpr int TCS_MAX_ND = 8;       // D <= 256
+constexpr int TCS_MAX_ES = 4;       // codebook stages
+// barrier slots of the streaming kernel
+constexpr int TCS_B_ZFULL = 0, TCS_B_ZEMPTY = 8, TCS_B_EFULL = 16, TCS_B_EEMPTY = 20, TCS_B_AFULL = 24, TCS_B_AEMPTY = 26,
+              TCS_B_TFULL = 28, TCS_B_TEMPTY = 30, TCS_B_ZN = 32, TCS_B_PFULL = 34, TCS_B_PEMPTY = 36, TCS_B_TMEM = 38;
+
+static TcsGeom tcs_geometry(int D, int K) {
+  TcsGeom g{};
+  g.ok = false;
+  g.BN = 32;
+  while (g.BN < K && g.BN < TC_MAXBN) g.BN <<= 1;
+  g.nb = (K + g.BN - 1) / g.BN;
+  g.nD = (D + TC_DCH - 1) / TC_DCH;
+  if (g.nD > TCS_MAX_ND || g.nb * g.BN > TC_SORT_MAX) return g;
+  const size_t estage = (size_t)g.BN * 128;
+  size_t off = 0;
+  g.off_z = off;    off += (size_t)g.nD * TC_TILE * 128;
+  g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
+  g.off_aaug = off; off += 4096;
+  g.off_e = off;
+  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = (size_t)TC_OUT_WARPS * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
+  const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
+  const size_t tail = sz_pub + sz_wl + sz_zn + sz_ctab + 512;
+  long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
+  int nes = (int)(room / (long long)estage);
+  if (nes > TCS_MAX_ES) nes = TCS_MAX_ES;
+  if (nes < 2) return g;
+  g.nes = nes;
+  off += (size_t)nes * estage;
+  g.off_pub = off;  off += sz_pub;
+  g.off_wl = off;   off += sz_wl;
+  g.off_zn = off;   off += sz_zn;
+  g.off_ctab = off; off += sz_ctab;
+  g.off_bar = off;  off += 512;
+  g.total = off + 1024;
+  g.ok = true;
+  return g;
+}
+
+struct TcsParams {
+  const float* z; const float* E; const float* e2; const float* eaug_img; const uint32_t* meta;
+  const int* perm; const uint32_t* rmax;
+  int B, D, H, W, HW, K;
+  int BN, nb, nD, nes;
+  int bn_shift, w_shift;
+  int tiles_per_img; int ntiles;
+  uint32_t off_z, off_e, off_aug, off_aaug, off_pub, off_wl, off_zn, off_ctab, off_bar;
+  int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
+  float* sums; float* sums_rep; int nrep;
+  int* fb_count; int* fb_rows;
+  float* dbg;
+};
+
+template <bool DBG, bool STATS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const TcsParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = (uint64_t*)(smem + P.off_bar);
+  const uint32_t bar0 = sbase + P.off_bar;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(bars + TCS_B_TMEM);
+  const int nD = P.nD, nes = P.nes;
+  const int ktot = P.nb * P.BN;
+  const uint32_t estage = (uint32_t)P.BN * 128;
+
+  if (threadIdx.x == 32) {
+    for (int c = 0; c < TCS_MAX_ND; ++c) { mbar_init(BAR(TCS_B_ZFULL + c), 1); mbar_init(BAR(TCS_B_ZEMPTY + c), TC_OUT_WARPS + 3); }
+    for (int e = 0; e < TCS_MAX_ES; ++e) { mbar_init(BAR(TCS_B_EFULL + e), 1); mbar_init(BAR(TCS_B_EEMPTY + e), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(TCS_B_AFULL + i), 1); mbar_init(BAR(TCS_B_AEMPTY + i), 1);
+      mbar_init(BAR(TCS_B_TFULL + i), 1); mbar_init(BAR(TCS_B_TEMPTY + i), TC_SCAN_WARPS);
+      mbar_init(BAR(TCS_B_ZN + i), 2);
+      mbar_init(BAR(TCS_B_PFULL + i), TC_SCAN_WARPS); mbar_init(BAR(TCS_B_PEMPTY + i), TC_OUT_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= TC_AUX_WARPS) {
+    const int t = threadIdx.x - 32 * TC_AUX_WARPS;
+    constexpr int NT = 32 * (TC_SCAN_WARPS + TC_OUT_WARPS);
+    float4* a = (float4*)(smem + P.off_aaug);
+    for (int i = t; i < 256; i += NT) {                   // ones block of the augmentation K-step (see the resident kernel)
+      const int row = (i >> 3) & 7;
+      const float v = row < 3 ? 1.f : 0.f;
+      a[i] = make_float4(v, v, v, v);
+    }
+    const float c1 = 0.00390625f * 1.03f;
+    const float c2 = (float)(P.D + 16) * 4.76837158e-7f;
+    for (int c = t; c < P.nb * (P.BN >> 5); c += NT) {
+      const float rm = __uint_as_float(P.rmax[c]);
+      ((float*)(smem + P.off_ctab))[2 * c] = 0.5f * (c1 + c2) * rm;
+      ((float*)(smem + P.off_ctab))[2 * c + 1] = 0.5f * c2 * rm * rm + 1e-30f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int ecount = 0, acount = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
+        for (int blk = 0; blk < P.nb; ++blk) {
+          {   // this block's -|e|^2/2 image
+            const int as = acount & 1;
+            mbar_wait_sleep(BAR(TCS_B_AEMPTY + as), ((acount >> 1) & 1) ^ 1, 64);
+            mbar_expect_tx(BAR(TCS_B_AFULL + as), (uint32_t)P.BN * 32);
+            bulk_load_1d(sbase + P.off_aug + (uint32_t)as * P.BN * 32, P.eaug_img + (size_t)blk * P.BN * 8, (uint32_t)P.BN * 32,
+                         BAR(TCS_B_AFULL + as));
+            ++acount;
+          }
+          for (int c = 0; c < nD; ++c) {
+            if (blk == 0) {                                // the z chunk of this tile (freed by the previous tile's readers)
+              mbar_wait_sleep(BAR(TCS_B_ZEMPTY + c), (it & 1) ^ 1, 64);
+              mbar_expect_tx(BAR(TCS_B_ZFULL + c), TC_TILE * 128);
+              for (int grp = 0; grp < 4; ++grp)
+                tma_load_3d(sbase + P.off_z + c * (TC_TILE * 128) + grp * 4096, &zmap, BAR(TCS_B_ZFULL + c),
+                            pt * TC_TILE + grp * 32, c * TC_DCH, b);
+            }
+            const int es = ecount % nes;
+            mbar_wait_sleep(BAR(TCS_B_EEMPTY + es), ((ecount / nes) & 1) ^ 1, 32);
+            mbar_expect_tx(BAR(TCS_B_EFULL + es), estage);
+            tma_load_2d(sbase + P.off_e + (uint32_t)es * estage, &emap, BAR(TCS_B_EFULL + es), c * TC_DCH, blk * P.BN);
+            ++ecount;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(P.BN);
+      int g = 0, ecount = 0, acount = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int blk = 0; blk < P.nb; ++blk, ++g) {
+          const int a = g & 1, aph = (g >> 1) & 1;
+          mbar_wait_sleep(BAR(TCS_B_TEMPTY + a), aph ^ 1, 32);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
+          uint32_t acc = 0;
+          for (int c = 0; c < nD; ++c) {
+            if (blk == 0) mbar_wait_sleep(BAR(TCS_B_ZFULL + c), it & 1, 32);
+            const int es = ecount % nes;
+            mbar_wait_sleep(BAR(TCS_B_EFULL + es), (ecount / nes) & 1, 32);
+            tc_fence_after();
+            const int ksteps = min(4, (P.D - c * TC_DCH + 7) >> 3);
+            const uint32_t zaddr = sbase + P.off_z + c * (TC_TILE * 128);
+            const uint32_t eaddr = sbase + P.off_e + (uint32_t)es * estage;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = make_desc(zaddr + ks * 1024, 4096, 512, 1);
+              const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
+              umma_tf32(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+            }
+            umma_commit(BAR(TCS_B_EEMPTY + es));           // codebook stage consumed
+            ++ecount;
+            if (blk == P.nb - 1) umma_commit(BAR(TCS_B_ZEMPTY + c));   // last use of this z chunk by the tensor core
+          }
+          {
+            const int as = acount & 1;
+            mbar_wait_sleep(BAR(TCS_B_AFULL + as), (acount >> 1) & 1, 32);
+            tc_fence_after();
+            const uint64_t ad = make_desc(sbase + P.off_aaug, 1024, 512, 1);
+            const uint64_t bd = make_desc(sbase + P.off_aug + (uint32_t)as * P.BN * 32, 128, 256, 0);
+            umma_tf32(d_tmem, ad, bd, idesc, acc);
+            umma_commit(BAR(TCS_B_AEMPTY + as));
+            ++acount;
+          }
+          umma_commit(BAR(TCS_B_TFULL + a));
+        }
+      }
+    }
+  } else if (warp < TC_AUX_WARPS) {
+    // ===================================== |z|^2 workers ====================================
+    const int pA = (warp - 2) * 64 + 2 * lane;
+    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
+    const uint32_t zn_s = sbase + P.off_zn;
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((pA & 31) >> 2) ^ (i << 1)) << 4);
+    for (int it = 0; it < my_tiles; ++it) {
+      float2 zz = make_float2(0.f, 0.f);
+      for (int c = 0; c < nD; ++c) {
+        mbar_wait(BAR(TCS_B_ZFULL + c), it & 1);
+        const uint32_t zc = zrow0 + (uint32_t)c * 16384;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 v = lds_v2(zc + jj * 512 + zx[i]);
+            zz = __ffma2_rn(v, v, zz);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(TCS_B_ZEMPTY + c));
+      }
+      const int sl = it & 1;
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(zn_s + (uint32_t)(sl * TC_TILE + pA) * 4), "f"(zz.x), "f"(zz.y) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(TCS_B_ZN + sl));
+    }
+  } else if (warp < TC_AUX_WARPS + TC_SCAN_WARPS) {
+    // ===================================== scan warps (as in the resident kernel) ==========================
+    const int quad = warp & 3, cg = (warp - TC_AUX_WARPS) >> 2;
+    const int p = quad * 32 + lane;
+    const uint32_t ctab_s = sbase + P.off_ctab;
+    const uint32_t zn_s = sbase + P.off_zn + (uint32_t)p * 4;
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)(cg * TC_TILE + p) * 16;
+    const int nchunks = P.BN >> 5;
+    int g = 0;
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // only for the debug dump
+    for (int it = 0; it < my_tiles; ++it) {
+      const int sl = it & 1, sph = (it >> 1) & 1;
+      mbar_wait(BAR(TCS_B_ZN + sl), sph);
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)sl * (TC_TILE * 4)));
+      const float zn = sqrtf(z2) * 1.00001f;
+      float L = -INFINITY, Urec = -INFINITY;
+      int cnt = 0;
+      uint32_t rcA = 0, rcB = 0, rm0 = 0, rm1 = 0;
+      for (int blk = 0; blk < P.nb; ++blk, ++g) {
+        const int a = g & 1, aph = (g >> 1) & 1;
+        mbar_wait(BAR(TCS_B_TFULL + a), aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
+        for (int c = cg; c < nchunks; c += TC_NCG) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          const int gc = blk * nchunks + c;
+          float cA, cB;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)gc * 8));
+          const float delta = __fmaf_rn(zn, cA, cB);
+          tmem_ld_wait();
+          if (DBG) {
+            float* o = P.dbg + ((size_t)tb * P.HW + tpt * TC_TILE + p) * ktot + gc * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = v[j];
+          }
+          float m4[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float m = fmaxf(fmaxf(v[8 * h], v[8 * h + 1]), v[8 * h + 2]);
+            m = fmaxf(fmaxf(m, v[8 * h + 3]), v[8 * h + 4]);
+            m = fmaxf(fmaxf(m, v[8 * h + 5]), v[8 * h + 6]);
+            m4[h] = fmaxf(m, v[8 * h + 7]);
+          }
+          const float cm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          L = fmaxf(L, cm - delta);
+          if (Urec < L) { cnt = 0; Urec = -INFINITY; }
+          const float T = L - delta;
+          const float2 nT2 = make_float2(-T, -T);
+          uint32_t n4[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t nm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float2 d2 = __fadd2_rn(make_float2(v[8 * h + j], v[8 * h + j + 1]), nT2);
+              nm = __funnelshift_l(__float_as_uint(d2.x), nm, 1);
+              nm = __funnelshift_l(__float_as_uint(d2.y), nm, 1);
+            }
+            n4[h] = nm;
+          }
+          const uint32_t cand = ~((n4[0] << 24) | (n4[1] << 16) | (n4[2] << 8) | n4[3]);
+          const bool has = cand != 0u;
+          const bool s0 = has && cnt == 0, s1 = has && cnt == 1;
+          rcA = s0 ? (uint32_t)gc : rcA; rm0 = s0 ? cand : rm0;
+          rcB = s1 ? (uint32_t)gc : rcB; rm1 = s1 ? cand : rm1;
+          cnt += has ? 1 : 0;
+          Urec = has ? fmaxf(Urec, cm + delta) : Urec;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(TCS_B_TEMPTY + a));
+      }
+      if (DBG) { tpt += (int)gridDim.x; while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; } }
+      if (cnt < 2) rm1 = 0;
+      if (cnt < 1) rm0 = 0;
+      const uint32_t w1 = f32_up16(Urec) | (rcA << 8) | (rcB << 1) | (cnt > 2 ? 1u : 0u);
+      const int par = it & 1, pph = (it >> 1) & 1;
+      mbar_wait(BAR(TCS_B_PEMPTY + par), pph ^ 1);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_s + (uint32_t)par * (TC_NCG * TC_TILE * 16)),
+                   "r"(__float_as_uint(L)), "r"(w1), "r"(rm0), "r"(rm1) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(TCS_B_PFULL + par));
+    }
+  } else {
+    // ===================================== output warps =====================================
+    const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
+    const int px = lane & 15, hf = lane >> 4;
+    const int p = ow * 16 + px;
+    const float rminbig = __uint_as_float(P.meta[1]);
+    const int D = P.D, nq = D >> 2;
+    const uint32_t zrow = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
+    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TC_WLCAP * 4);
+    const uint32_t zn_s = sbase + P.off_zn;
+    float* sums_mine = nullptr;
+    if (STATS) {
+      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
+      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * D;
+    }
+    const size_t hw = (size_t)P.HW;
+    const size_t img_stride = (size_t)D * hw;
+    float2 ls2 = make_float2(0.f, 0.f);
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int sl = it & 1, sph = (it >> 1) & 1;
+      const int b = tb, p0 = tpt * TC_TILE;
+      tpt += (int)gridDim.x;
+      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
+      for (int c = 0; c < nD; ++c) mbar_wait(BAR(TCS_B_ZFULL + c), it & 1);   // z chunks visible to this thread
+      mbar_wait(BAR(TCS_B_ZN + sl), sph);
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)(sl * TC_TILE + p) * 4));
+      mbar_wait(BAR(TCS_B_PFULL + sl), sph);
+      const float zn = sqrtf(z2) * 1.00001f;
+      const bool bad = !(z2 <= 3.0e38f);
+      uint32_t pw[TC_NCG][4];
+      float Lg = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < TC_NCG; ++i) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pw[i][0]), "=r"(pw[i][1]), "=r"(pw[i][2]), "=r"(pw[i][3])
+                     : "r"(pub_s + (uint32_t)(sl * TC_NCG + i) * (TC_TILE * 16)));
+        Lg = fmaxf(Lg, __uint_as_float(pw[i][0]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(TCS_B_PEMPTY + sl));
+      int total = 0;
+      bool ovf = false;
+#pragma unroll
+      for (int i = 0; i < TC_NCG; ++i) {
+        const bool al = __uint_as_float(pw[i][1] & 0xFFFF0000u) >= Lg;
+        if (!al) { pw[i][2] = 0; pw[i][3] = 0; }
+        else ovf |= (pw[i][1] & 1u) != 0;
+        total += __popc(pw[i][2]) + __popc(pw[i][3]);
+      }
+      const float lbest = 2.f * Lg;
+      bool big_safe = true;
+      if (rminbig < 3.0e38f) {
+        const float bigub = rminbig * (2.f * zn - rminbig);
+        big_safe = (rminbig >= zn) && (bigub + 1e-5f * (fabsf(bigub) + fabsf(lbest)) < lbest);
+      }
+      bool fb = bad || ovf || total == 0 || !big_safe;
+      int w = 0;
+      if (total == 1) {
+#pragma unroll
+        for (int i = 0; i < TC_NCG; ++i) {
+          if (pw[i][2]) w = (int)(((pw[i][1] >> 8) & 0x7Fu) * 32u) + __clz(pw[i][2]);
+          if (pw[i][3]) w = (int)(((pw[i][1] >> 1) & 0x7Fu) * 32u) + __clz(pw[i][3]);
+        }
+      }
+      int worig = __ldg(P.perm + w);
+      // ---- pixels with several candidates: exact fp32 re-rank, code rows from global memory ----------------
+      const int mine = (!fb && total > 1 && hf == 0) ? total : 0;
+      int pos = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += t;
+      }
+      const int npairs = __shfl_sync(0xffffffffu, pos, 31);
+      pos -= mine;
+      if (npairs > 0) {
+        if (mine > 0) {
+          if (pos + mine > TC_WLCAP) {
+            fb = true;
+          } else {
+            uint32_t wa = wl_s + (uint32_t)pos * 4;
+#pragma unroll
+            for (int i = 0; i < TC_NCG; ++i) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                uint32_t m = pw[i][2 + r];
+                const uint32_t base = ((uint32_t)px << 16) | (((pw[i][1] >> (r ? 1 : 8)) & 0x7Fu) * 32u);
+                while (m) {
+                  const int jb = __clz(m);
+                  m &= ~(0x80000000u >> jb);
+                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
+                  wa += 4;
+                }
+              }
+            }
+          }
+        }
+        const uint32_t fbm = __ballot_sync(0xffffffffu, fb && hf == 0);
+        fb = ((fbm >> px) & 1u) != 0;
+        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TC_WLCAP) ? pos : npairs);
+        __syncwarp();
+        unsigned long long key = 0ull;
+        for (int i0 = 0; i0 < nlist; i0 += 32) {
+          const int i = i0 + lane;
+          unsigned long long kcur = 0ull;
+          if (i < nlist) {
+            uint32_t item;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
+            const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
+            const int pp = ow * 16 + ppx;
+            const int korig = __ldg(P.perm + k);
+            const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
+            const uint32_t zr = sbase + P.off_z + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
+            const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
+            const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
+            float dot = 0.f;
+            for (int j0 = 0; j0 < nq; j0 += 4) {          // four quads' loads, then their sixteen chained fmas
+              float4 e4[4];
+              float zv[4][4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int j = j0 + t;
+                const bool in = j < nq;
+                e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t zo = (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+                zv[t][0] = in ? lds_f32(x0 + zo) : 0.f; zv[t][1] = in ? lds_f32(x1 + zo) : 0.f;
+                zv[t][2] = in ? lds_f32(x2 + zo) : 0.f; zv[t][3] = in ? lds_f32(x3 + zo) : 0.f;
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (j0 + t < nq) {
+                  dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
+                  dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
+                  dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
+                  dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
+                }
+              }
+            }
+            const float sc = ref_score(dot, __ldg(P.e2 + korig), lds_f32(zn_s + (uint32_t)(sl * TC_TILE + pp) * 4));
+            kcur = ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)korig) << 16) |
+                   (unsigned long long)k;
+          }
+          const int rel = pos - i0;
+          const int maxmine = __reduce_max_sync(0xffffffffu, mine);
+          for (int t = 0; t < maxmine; ++t) {
+            const int src = rel + t;
+            const bool take = t < mine && src >= 0 && src < 32;
+            const unsigned long long kk = __shfl_sync(0xffffffffu, kcur, take ? src : 0);
+            if (take && kk > key) key = kk;
+          }
+        }
+        const unsigned long long kp = __shfl_sync(0xffffffffu, key, px);
+        if (total > 1 && !fb) worig = 0xFFFF - (int)((kp >> 16) & 0xFFFFull);
+      }
+
+      // ---- outputs, chunk by chunk; each z chunk goes back to the producer as soon as this warp is done with it ----
+      const int pp = p0 + p;
+      if (fb) {
+        if (hf == 0) {
+          const int slot = atomicAdd(P.fb_count, 1);
+          P.fb_rows[slot] = b * P.HW + pp;
+        }
+      } else if (hf == 0) {
+        int h, wc;
+        if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
+        else { h = pp / P.W; wc = pp - h * P.W; }
+        const size_t nb_ = (size_t)b * hw;
+        if (P.ids) P.ids[nb_ + (size_t)(wc * P.H + h)] = (int64_t)worig;
+        if (P.ids_nat) P.ids_nat[nb_ + pp] = worig;
+        if (STATS) atomicAdd(&P.counts[worig], 1);
+      }
+      const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)worig * D);
+      float* qo = P.q + (size_t)b * img_stride + pp;
+      float* so = STATS ? sums_mine + (size_t)worig * D : nullptr;
+      for (int c = 0; c < nD; ++c) {
+        if (!fb) {
+          float4 e4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {                   // quads j = 8c + 2t + hf of this chunk
+            const int j = 8 * c + 2 * t + hf;
+            e4[t] = j < nq ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = 8 * c + 2 * t + hf;
+            if (j < nq) {
+              const uint32_t zj = zrow + (uint32_t)c * 16384 + (uint32_t)(2 * t + hf) * 512;
+              const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
+              const float2 m1 = make_float2(-1.f, -1.f);
+              const float2 d01 = __ffma2_rn(make_float2(e4[t].x, e4[t].y), m1, make_float2(z0, z1));
+              const float2 d23 = __ffma2_rn(make_float2(e4[t].z, e4[t].w), m1, make_float2(z2v, z3));
+              ls2 = __ffma2_rn(d01, d01, ls2);
+              ls2 = __ffma2_rn(d23, d23, ls2);
+              if (!DBG || P.q) {
+                float* qj = qo + (size_t)(4 * j) * hw;
+                __stcs(qj, e4[t].x);
+                __stcs(qj + hw, e4[t].y);
+                __stcs(qj + 2 * hw, e4[t].z);
+                __stcs(qj + 3 * hw, e4[t].w);
+              }
+              if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(TCS_B_ZEMPTY + c));
+      }
+    }
+    float lsum = ls2.x + ls2.y;
+    lsum = warp_sum(lsum);
+    if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1011,9 +1549,14 @@ static int sm_count_tc() {
   return n;
 }
 
+static bool tcs_supported(int D, int K) { return tcs_geometry(D, K).ok; }
+
+static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
+
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
   const TcGeom g = tc_geometry(a.D, a.K);
+  if (!(g.ok && g.nb * g.BN <= TC_SORT_MAX) && tcs_supported(a.D, a.K)) return launch_assign_tcs_impl(a, dbg, s);
   VQ_REQUIRE(g.ok && g.nb * g.BN <= TC_SORT_MAX && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
   VQ_REQUIRE(a.q != nullptr || dbg != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
   EncodeTiledFn enc = get_encode_fn();
@@ -1098,6 +1641,87 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   return VQ_OK;
 }
 
+static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
+  const int HW = a.H * a.W;
+  const TcsGeom g = tcs_geometry(a.D, a.K);
+  VQ_REQUIRE(g.ok && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path (streamed codebook): unsupported shape");
+  VQ_REQUIRE(a.q != nullptr || dbg != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
+  EncodeTiledFn enc = get_encode_fn();
+  VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
+             "tensor-core path: z / embed must be 16-byte aligned");
+  CUtensorMap zmap, emap;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
+    cuuint32_t box[3] = {32, TC_DCH, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)(g.nb * g.BN)};
+    cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
+    cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
+  }
+  float* eaug_img = a.ws.tc_aug;
+  uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
+  uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
+  const int ktot = g.nb * g.BN;
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+      a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+
+  TcsParams P{};
+  P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
+  P.perm = a.ws.tc_perm; P.rmax = rmax;
+  P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
+  P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nes = g.nes;
+  P.bn_shift = 0;
+  while ((1 << P.bn_shift) < g.BN) ++P.bn_shift;
+  P.w_shift = -1;
+  if ((a.W & (a.W - 1)) == 0) { P.w_shift = 0; while ((1 << P.w_shift) < a.W) ++P.w_shift; }
+  P.tiles_per_img = HW / TC_TILE;
+  P.ntiles = a.B * P.tiles_per_img;
+  P.off_z = (uint32_t)g.off_z; P.off_e = (uint32_t)g.off_e; P.off_aug = (uint32_t)g.off_aug; P.off_aaug = (uint32_t)g.off_aaug;
+  P.off_pub = (uint32_t)g.off_pub; P.off_wl = (uint32_t)g.off_wl; P.off_zn = (uint32_t)g.off_zn;
+  P.off_ctab = (uint32_t)g.off_ctab; P.off_bar = (uint32_t)g.off_bar;
+  P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
+  P.counts = a.stats ? a.ws.counts : nullptr;
+  P.sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
+  P.sums_rep = a.ws.sums_rep;
+  P.nrep = tc_sums_replicas(a.K, a.D);
+  P.fb_count = a.ws.misc; P.fb_rows = a.ws.fb_rows;
+  P.dbg = dbg;
+
+  int grid = sm_count_tc();
+  if (grid > P.ntiles) grid = P.ntiles;
+  const bool stats = a.stats != nullptr;
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const TcsParams);
+  KernFn kern = dbg ? (stats ? vq_assign_tcs_kernel<true, true> : vq_assign_tcs_kernel<true, false>)
+                    : (stats ? vq_assign_tcs_kernel<false, true> : vq_assign_tcs_kernel<false, false>);
+  const int ki = (dbg ? 2 : 0) + (stats ? 1 : 0);
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[ki]) {
+    VQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_set[ki] = true;
+  }
+  const bool prof = profile_begin(s);
+  kern<<<grid, TC_THREADS, g.total, s>>>(zmap, emap, P);
+  if (prof) profile_end(s);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
 int launch_assign_tc(const FwdArgs& a, cudaStream_t s) { return launch_assign_tc_impl(a, nullptr, s); }
 
 int tc_debug_timing(long long* host_out, int n) {
@@ -1114,7 +1738,9 @@ int tc_debug_timing(long long* host_out, int n) {
 
 int tc_debug_ncols(int D, int K) {
   const TcGeom g = tc_geometry(D, K);
-  return g.ok ? g.nb * g.BN : 0;
+  if (g.ok && g.nb * g.BN <= TC_SORT_MAX) return g.nb * g.BN;
+  const TcsGeom gs = tcs_geometry(D, K);
+  return gs.ok ? gs.nb * gs.BN : 0;
 }
 
 }  // namespace vqb200
