@@ -127,6 +127,10 @@ def cpu_step_factory(wl, slices):
     D, H, K = wl["D"], wl["H"], wl["K"]
     m = OracleVQ(D, K, CFG["momentum"], CFG["eps"], "torch", chunk=65536)
     m.train(True)
+    with torch.no_grad():       # same warmed EMA state as the B200 arm
+        cs = torch.rand(K, generator=torch.Generator().manual_seed(1234)) * (slices * H * H / K) + 1.0
+        m.cluster_size.copy_(cs)
+        m.embed_avg.copy_((m.embed * cs[:, None]).T)
     zs = [torch.randn(slices, D, H, H, generator=g) for _ in range(2)]
     g_q = torch.randn(slices, D, H, H, generator=g)
     one = torch.ones(())
@@ -222,6 +226,15 @@ def run_b200_arm(args, wl, wl_name):
     if args.simt:
         vq.kernel_flags = 1
     vq.train(True)
+    if not args.cold:
+        # steady-state ("warmed") EMA state of SURVEY 8(d): cluster_size = rand(K) * N/K + 1 and a consistent
+        # embed_avg = embed * cluster_size, instead of the first-step state (cluster_size = 0) whose update blows
+        # the unused codes up by ~1e5 -- that transient is covered by the parity tests
+        with torch.no_grad():
+            gcpu = torch.Generator().manual_seed(1234)
+            cs = torch.rand(K, generator=gcpu) * (world * n_per_gpu / K) + 1.0
+            vq.cluster_size.copy_(cs.to(dev))
+            vq.embed_avg.copy_((vq.embed * vq.cluster_size[:, None]).T)
     if world > 1:      # identical codebooks on every rank (DDP would broadcast rank 0's buffers once)
         for b in vq.buffers():
             dist.broadcast(b, 0)
@@ -310,6 +323,13 @@ def run_b200_arm(args, wl, wl_name):
         f1.record()
         barrier()
         eval_ms = f0.elapsed_time(f1) / fsteps
+        # rows of the last forward that the tensor-core search handed to the exhaustive fp32 fallback
+        from medical_image_editing_b200.src.functions import vq_function as _vf
+        fb_rows = None
+        if path == 1:
+            wsb = _vf._WORKSPACES.get((dev.index, torch.cuda.current_stream().cuda_stream))
+            if wsb is not None:
+                fb_rows = int(L.vq_debug_fallback_rows(wsb.data_ptr(), n_per_gpu, K, D, torch.cuda.current_stream().cuda_stream))
     vq.train(True)
 
     if rank == 0:
@@ -338,7 +358,8 @@ def run_b200_arm(args, wl, wl_name):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl, wl_name, world, extra={"search_path": "tcgen05+fp32-rerank" if path == 1 else "fp32-cuda-core"}),
+            "config": workload_config(wl, wl_name, world, extra={"search_path": "tcgen05+fp32-rerank" if path == 1 else "fp32-cuda-core",
+                                                          "ema_state": "cold" if args.cold else "warmed"}),
             "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
@@ -346,7 +367,8 @@ def run_b200_arm(args, wl, wl_name):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms},
+            "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms,
+                             "fallback_rows": fb_rows},
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -362,6 +384,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]

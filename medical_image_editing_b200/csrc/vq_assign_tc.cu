@@ -998,6 +998,7 @@ struct TcsGeom {
 };
 constexpr int TCS_MAX_ND = 8;       // D <= 256
 constexpr int TCS_MAX_ES = 4;       // codebook stages
+constexpr int TCS_WLCAP = 64;       // (pixel, code) pairs per output warp and tile (large codebooks tie more often)
 // barrier slots of the streaming kernel
 constexpr int TCS_B_ZFULL = 0, TCS_B_ZEMPTY = 8, TCS_B_EFULL = 16, TCS_B_EEMPTY = 20, TCS_B_AFULL = 24, TCS_B_AEMPTY = 26,
               TCS_B_TFULL = 28, TCS_B_TEMPTY = 30, TCS_B_ZN = 32, TCS_B_PFULL = 34, TCS_B_PEMPTY = 36, TCS_B_TMEM = 38;
@@ -1016,7 +1017,7 @@ static TcsGeom tcs_geometry(int D, int K) {
   g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
   g.off_aaug = off; off += 4096;
   g.off_e = off;
-  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = (size_t)TC_OUT_WARPS * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
+  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = (size_t)TC_OUT_WARPS * TCS_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
   const size_t tail = sz_pub + sz_wl + sz_zn + sz_ctab + 512;
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
@@ -1306,7 +1307,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
-    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TC_WLCAP * 4);
+    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TCS_WLCAP * 4);
     const uint32_t zn_s = sbase + P.off_zn;
     float* sums_mine = nullptr;
     if (STATS) {
@@ -1376,7 +1377,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       pos -= mine;
       if (npairs > 0) {
         if (mine > 0) {
-          if (pos + mine > TC_WLCAP) {
+          if (pos + mine > TCS_WLCAP) {
             fb = true;
           } else {
             uint32_t wa = wl_s + (uint32_t)pos * 4;
@@ -1398,7 +1399,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
         const uint32_t fbm = __ballot_sync(0xffffffffu, fb && hf == 0);
         fb = ((fbm >> px) & 1u) != 0;
-        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TC_WLCAP) ? pos : npairs);
+        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TCS_WLCAP) ? pos : npairs);
         __syncwarp();
         unsigned long long key = 0ull;
         for (int i0 = 0; i0 < nlist; i0 += 32) {
