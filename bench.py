@@ -236,8 +236,8 @@ def run_b200_arm(args, wl, wl_name):
             vq.cluster_size.copy_(cs.to(dev))
             vq.embed_avg.copy_((vq.embed * vq.cluster_size[:, None]).T)
     if world > 1:      # identical codebooks on every rank (DDP would broadcast rank 0's buffers once)
-        for b in vq.buffers():
-            dist.broadcast(b, 0)
+        from medical_image_editing_b200.src.trainers import broadcast_module_state
+        broadcast_module_state(vq, 0)
     path = L.vq_assign_path(B, D, H, H, K, vq.kernel_flags)
 
     def step(i):
@@ -349,7 +349,15 @@ def run_b200_arm(args, wl, wl_name):
             else:
                 ach = alg_flops / (avg_kernel_ms * 1e-3) / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16}
-            roof.update({"traffic": None, "kernel": "vq_assign_tc" if path == 1 else "vq_assign_simt",
+            traffic = None
+            try:        # measured DRAM bytes per launch of this workload's search kernel (one ncu --set full capture)
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tj = json.load(f).get(wl_name)
+                if tj and path == 1:
+                    traffic = tj["bytes"]
+            except Exception:
+                traffic = None
+            roof.update({"traffic": traffic, "kernel": "vq_assign_tc" if path == 1 else "vq_assign_simt",
                          "kernel_ms": avg_kernel_ms, "launches_timed": nl.value,
                          "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                          "peak_source": f"MEASURED_PEAKS.json ({which})"})

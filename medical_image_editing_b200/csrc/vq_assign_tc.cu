@@ -88,8 +88,9 @@ static TcGeom tc_geometry(int D, int K) {
 }
 
 int tc_sums_replicas(int K, int D) {
-  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 4 MB in total
-  size_t r = ((size_t)4 << 20) / ((size_t)K * D * 4);
+  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 1 MB in total (the replicas
+  // are zeroed by vq_prep_kernel and folded by vq_finish_kernel on every call)
+  size_t r = ((size_t)1 << 20) / ((size_t)K * D * 4);
   if (r > (size_t)TC_MAX_REP) r = TC_MAX_REP;
   if (r < 1) r = 1;
   return (int)r;
