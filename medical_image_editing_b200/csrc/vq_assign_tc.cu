@@ -34,9 +34,19 @@ namespace vqb200 {
 constexpr int TC_TILE = 128;        // pixels per tile (UMMA M)
 constexpr int TC_MAXBN = 256;       // codes per accumulator stage (UMMA N)
 constexpr int TC_DCH = 32;          // channels per shared-memory chunk (128-byte swizzle rows)
-constexpr int TC_NCG = 2;           // column groups: scan warps per TMEM lane quadrant
+#ifndef VQ_TC_NCG
+#define VQ_TC_NCG 2
+#endif
+#ifndef VQ_TC_OPX_SHIFT
+#define VQ_TC_OPX_SHIFT 4
+#endif
+constexpr int TC_NCG = VQ_TC_NCG;   // column groups: scan warps per TMEM lane quadrant
 constexpr int TC_SCAN_WARPS = 4 * TC_NCG;
-constexpr int TC_OUT_WARPS = 8;     // 16 pixels of the tile each
+constexpr int TC_OPX_SHIFT = VQ_TC_OPX_SHIFT;
+constexpr int TC_OPX = 1 << TC_OPX_SHIFT;        // pixels per output warp
+constexpr int TC_OUT_WARPS = 128 / TC_OPX;       // TC_OPX pixels of the tile each
+constexpr int TC_OCS = 32 / TC_OPX;              // lanes per pixel = channel splits (4): lane = px + TC_OPX * hf
+static_assert((1 << TC_OPX_SHIFT) == TC_OPX && TC_OPX * TC_OCS == 32 && 8 % TC_OCS == 0, "output-warp lane mapping");
 constexpr int TC_AUX_WARPS = 4;     // TMA producer, MMA issuer, two |z|^2 workers
 constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_SCAN_WARPS + TC_OUT_WARPS);
 constexpr int TC_WLCAP = 32;        // (pixel, code) pairs re-scored exactly per output warp and tile
@@ -88,9 +98,9 @@ static TcGeom tc_geometry(int D, int K) {
 }
 
 int tc_sums_replicas(int K, int D) {
-  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 1 MB in total (the replicas
+  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 4 MB in total (the replicas
   // are zeroed by vq_prep_kernel and folded by vq_finish_kernel on every call)
-  size_t r = ((size_t)1 << 20) / ((size_t)K * D * 4);
+  size_t r = ((size_t)4 << 20) / ((size_t)K * D * 4);
   if (r > (size_t)TC_MAX_REP) r = TC_MAX_REP;
   if (r < 1) r = 1;
   return (int)r;
@@ -363,6 +373,13 @@ __device__ __forceinline__ uint32_t zs_off(int p, int d) {
                     ((((p & 31) >> 2) ^ ((row & 3) << 1)) << 4) + ((p & 3) << 2));
 }
 
+// 1.0f if x < 0 (any negative normal number), else 0.0f -- one saturating multiply on the fp32 pipe.  .ftz flushes a
+// denormal x to zero, so the result is exactly 0 or 1 (a difference that small is far inside the bound's slack).
+__device__ __forceinline__ float sign01(float x) {
+  float r;
+  asm("mul.ftz.sat.f32 %0, %1, 0fFE800000;" : "=f"(r) : "f"(x));      // x * -2^126, clamped to [0, 1]
+  return r;
+}
 __device__ __forceinline__ uint32_t f32_orderable(float x) {   // monotone map float -> uint32
   const uint32_t u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -560,7 +577,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     }
   } else if (warp < TC_AUX_WARPS + TC_SCAN_WARPS) {
     // ===================================== scan warps =======================================
-    // warp = (TMEM lane quadrant, column group): thread = (pixel, half of the 32-code chunks).  Running max and
+    // warp = (TMEM lane quadrant, column group): thread = (pixel, 1/TC_NCG of the 32-code chunks).  Running max and
     // sign-bit candidate masks over the accumulators; the result (bounds + <= 2 candidate chunks) is published in
     // shared memory for the output warps.  No exact arithmetic, no synchronisation with sibling warps.
     const int quad = warp & 3, cg = (warp - TC_AUX_WARPS) >> 2;
@@ -620,17 +637,30 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           if (Urec < L) { cnt = 0; Urec = -INFINITY; }    // nothing recorded so far can still win
           const float T = L - delta;
           const float2 nT2 = make_float2(-T, -T);
+          // "below threshold" bits of the 32 columns.  The integer pipe (funnel shifts) and the fp32 pipe (saturating
+          // multiply -> exact 0/1, then acc = 2*acc + bit) each build half of them, so the two pipes work in parallel.
           uint32_t n4[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {                   // four independent sign-bit chains
-            uint32_t nm = 0;
+          for (int h = 0; h < 4; ++h) {
+            if (h & 1) {                                  // columns 8h..8h+7 on the fp32 pipe
+              float facc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float2 d2 = __fadd2_rn(make_float2(v[8 * h + j], v[8 * h + j + 1]), nT2);
-              nm = __funnelshift_l(__float_as_uint(d2.x), nm, 1);
-              nm = __funnelshift_l(__float_as_uint(d2.y), nm, 1);
+              for (int j = 0; j < 8; j += 2) {
+                const float2 d2 = __fadd2_rn(make_float2(v[8 * h + j], v[8 * h + j + 1]), nT2);
+                facc = __fmaf_rn(facc, 2.f, sign01(d2.x));
+                facc = __fmaf_rn(facc, 2.f, sign01(d2.y));
+              }
+              n4[h] = (uint32_t)facc;                     // exact: 8 bits
+            } else {                                      // columns 8h..8h+7 on the integer pipe
+              uint32_t nm = 0;
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float2 d2 = __fadd2_rn(make_float2(v[8 * h + j], v[8 * h + j + 1]), nT2);
+                nm = __funnelshift_l(__float_as_uint(d2.x), nm, 1);
+                nm = __funnelshift_l(__float_as_uint(d2.y), nm, 1);
+              }
+              n4[h] = nm;
             }
-            n4[h] = nm;
           }
           const uint32_t nmall = (n4[0] << 24) | (n4[1] << 16) | (n4[2] << 8) | n4[3];
           const uint32_t cand = ~nmall;                   // bit (31-j) set <=> column j is within the bound
@@ -676,17 +706,17 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     TC_TIMING_STORE(warp - TC_AUX_WARPS, my_tiles);
   } else {
     // ===================================== output warps =====================================
-    // warp ow owns pixels 16*ow .. 16*ow+15 of the tile; lane = (pixel px, channel half hf): all decisions for a
+    // warp ow owns TC_OPX pixels of the tile; lane = (pixel px, channel split hf): all decisions for a
     // pixel are taken inside one warp.  Per tile: merge the scan warps' bounds -> single candidate or a list of
     // (pixel, code) pairs -> exact fp32 re-rank of the pairs (one lane per pair, ascending-d fma chain) -> ids, q,
-    // (z-q)^2, EMA statistics for the channel quads j == hf (mod 2).
+    // (z-q)^2, EMA statistics for the channel quads j == hf (mod TC_OCS).
     // ZREG (emb_dim known at compile time, <= 64): the thread keeps its 4*NZQ z values in registers, so the z stage
     // goes back to the TMA producer before the scan results even arrive; the re-rank reads z through shuffles.
-    constexpr bool ZREG = DT != 0 && DT % 8 == 0 && DT <= 64;
-    constexpr int NZQ = ZREG ? DT / 8 : 1;                // channel quads per thread
+    constexpr bool ZREG = DT != 0 && DT % (4 * TC_OCS) == 0 && DT / (4 * TC_OCS) <= 8;
+    constexpr int NZQ = ZREG ? DT / (4 * TC_OCS) : 1;     // channel quads per thread
     const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
-    const int px = lane & 15, hf = lane >> 4;
-    const int p = ow * 16 + px;                           // pixel within the tile
+    const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
+    const int p = ow * TC_OPX + px;                           // pixel within the tile
     const float rminbig = __uint_as_float(P.meta[1]);   // +inf when no code is excluded
     const int bnsh = P.bn_shift;                          // BN == 1 << bnsh
     const uint32_t bn128 = (uint32_t)P.BN * 128;
@@ -722,13 +752,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       const uint32_t zrow = zrow0 + zst;
       TC_TICK(4);
       mbar_wait(BAR(1 + s), ph);                          // z tile (TMA writes) visible to this thread
-      float zq[NZQ][4];                                   // ZREG: z of channels 4*(2t+hf)+i
+      float zq[NZQ][4];                                   // ZREG: z of channels 4*(TC_OCS*t+hf)+i
       if (ZREG) {
 #pragma unroll
         for (int t = 0; t < NZQ; ++t) {
-          const int j = 2 * t + hf;                       // hf is not a compile-time constant: address arithmetic
-          const uint32_t zj = zrow + (uint32_t)(t >> 2) * 16384 + (uint32_t)((2 * t) & 7) * 512 + (uint32_t)hf * 512;
-          (void)j;
+          // quad j = TC_OCS * t + hf (hf < TC_OCS divides 8): chunk and quad-in-chunk of TC_OCS * t, plus hf
+          const uint32_t zj = zrow + (uint32_t)((TC_OCS * t) >> 3) * 16384 + (uint32_t)((TC_OCS * t) & 7) * 512 + (uint32_t)hf * 512;
 #pragma unroll
           for (int i = 0; i < 4; ++i) zq[t][i] = lds_f32(zj + zx[i]);
         }
@@ -794,7 +823,11 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
       }
       const int npairs = __shfl_sync(0xffffffffu, pos, 31);
       pos -= mine;                                                      // exclusive
+#ifdef VQ_ABL_NORERANK
+      if (false) {
+#else
       if (npairs > 0) {
+#endif
         if (mine > 0) {
           if (pos + mine > TC_WLCAP) {
             fb = true;                                    // list full: exhaustive search for this pixel
@@ -828,21 +861,21 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           uint32_t item = 0;                              // idle lanes score (pixel 0, code 0) and drop the result
           if (act) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
           const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-          const int pp = ow * 16 + ppx;
+          const int pp = ow * TC_OPX + ppx;
           const int kb = k >> bnsh, row = k & (P.BN - 1);
           uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
           const uint32_t r7 = (uint32_t)(row & 7) << 4;
           float dot = 0.f;
           if (ZREG) {
-            // z(pixel ppx, channel 4j+i) lives in lane ppx + 16*(j&1), register zq[j>>1][i]
+            // z(pixel ppx, channel 4j+i) lives in lane ppx + TC_OPX*(j % TC_OCS), register zq[j / TC_OCS][i]
 #pragma unroll
-            for (int j = 0; j < 2 * NZQ; ++j) {
+            for (int j = 0; j < TC_OCS * NZQ; ++j) {
               const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) << 4) ^ r7));
-              const int src = ppx + 16 * (j & 1);
-              const float z0 = __shfl_sync(0xffffffffu, zq[j >> 1][0], src);
-              const float z1 = __shfl_sync(0xffffffffu, zq[j >> 1][1], src);
-              const float z2s = __shfl_sync(0xffffffffu, zq[j >> 1][2], src);
-              const float z3 = __shfl_sync(0xffffffffu, zq[j >> 1][3], src);
+              const int src = ppx + TC_OPX * (j % TC_OCS);
+              const float z0 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][0], src);
+              const float z1 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][1], src);
+              const float z2s = __shfl_sync(0xffffffffu, zq[j / TC_OCS][2], src);
+              const float z3 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][3], src);
               dot = __fmaf_rn(z0, e4.x, dot);
               dot = __fmaf_rn(z1, e4.y, dot);
               dot = __fmaf_rn(z2s, e4.z, dot);
@@ -897,7 +930,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
             if (take && kk > key) key = kk;
           }
         }
-        // hand the winner to the partner lane (hf == 1) of the pixel
+        // hand the winner to the partner lanes (hf > 0) of the pixel
         const unsigned long long kp = __shfl_sync(0xffffffffu, key, px);
         if (total > 1 && !fb) w = (int)(kp & 0xFFFFull);
       }
@@ -927,7 +960,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
         const int kb = w >> bnsh, row = w & (P.BN - 1);
         const uint32_t r7 = (uint32_t)(row & 7);
-        // channel quads j = 2t + hf: chunk j >> 3, quad-in-chunk j & 7
+        // channel quads j = TC_OCS*t + hf: chunk j >> 3, quad-in-chunk j & 7
         const uint32_t ea = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
         float* qo = P.q + (size_t)b * img_stride + pp;
         float* so = STATS ? sums_mine + (size_t)worig * Dc : nullptr;
@@ -938,7 +971,12 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           const float2 d23 = __ffma2_rn(make_float2(e4.z, e4.w), m1, make_float2(z2v, z3));
           ls2 = __ffma2_rn(d01, d01, ls2);
           ls2 = __ffma2_rn(d23, d23, ls2);
-          if (!DBG || P.q) {
+#ifndef VQ_ABL_NOQ
+          if (!DBG || P.q)
+#else
+          if (false)
+#endif
+          {
             float* qj = qo + (size_t)(4 * j) * hw;
             __stcs(qj, e4.x);
             __stcs(qj + hw, e4.y);
@@ -947,16 +985,18 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           }
           if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
         };
+#ifndef VQ_ABL_NOOUT
         if (ZREG) {
 #pragma unroll
-          for (int t = 0; t < NZQ; ++t) quad_out(2 * t + hf, zq[t][0], zq[t][1], zq[t][2], zq[t][3]);
+          for (int t = 0; t < NZQ; ++t) quad_out(TC_OCS * t + hf, zq[t][0], zq[t][1], zq[t][2], zq[t][3]);
         } else {
 #pragma unroll 1
-          for (int j = hf; j < nq; j += 2) {
+          for (int j = hf; j < nq; j += TC_OCS) {
             const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
             quad_out(j, lds_f32(zj + zx[0]), lds_f32(zj + zx[1]), lds_f32(zj + zx[2]), lds_f32(zj + zx[3]));
           }
         }
+#endif
       }
       if (!ZREG) {
         __syncwarp();
@@ -1299,8 +1339,8 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
   } else {
     // ===================================== output warps =====================================
     const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
-    const int px = lane & 15, hf = lane >> 4;
-    const int p = ow * 16 + px;
+    const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
+    const int p = ow * TC_OPX + px;
     const float rminbig = __uint_as_float(P.meta[1]);
     const int D = P.D, nq = D >> 2;
     const uint32_t zrow = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
@@ -1410,7 +1450,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
             uint32_t item;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
             const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-            const int pp = ow * 16 + ppx;
+            const int pp = ow * TC_OPX + ppx;
             const int korig = __ldg(P.perm + k);
             const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
             const uint32_t zr = sbase + P.off_z + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
@@ -1477,17 +1517,17 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       float* so = STATS ? sums_mine + (size_t)worig * D : nullptr;
       for (int c = 0; c < nD; ++c) {
         if (!fb) {
-          float4 e4[4];
+          float4 e4[8 / TC_OCS];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {                   // quads j = 8c + 2t + hf of this chunk
-            const int j = 8 * c + 2 * t + hf;
+          for (int t = 0; t < 8 / TC_OCS; ++t) {          // quads j = 8c + TC_OCS*t + hf of this chunk
+            const int j = 8 * c + TC_OCS * t + hf;
             e4[t] = j < nq ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int j = 8 * c + 2 * t + hf;
+          for (int t = 0; t < 8 / TC_OCS; ++t) {
+            const int j = 8 * c + TC_OCS * t + hf;
             if (j < nq) {
-              const uint32_t zj = zrow + (uint32_t)c * 16384 + (uint32_t)(2 * t + hf) * 512;
+              const uint32_t zj = zrow + (uint32_t)c * 16384 + (uint32_t)(TC_OCS * t + hf) * 512;
               const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
               const float2 m1 = make_float2(-1.f, -1.f);
               const float2 d01 = __ffma2_rn(make_float2(e4[t].x, e4[t].y), m1, make_float2(z0, z1));
