@@ -46,10 +46,10 @@ constexpr int TC_OPX_SHIFT = VQ_TC_OPX_SHIFT;
 constexpr int TC_OPX = 1 << TC_OPX_SHIFT;        // pixels per output warp
 constexpr int TC_OUT_WARPS = 128 / TC_OPX;       // TC_OPX pixels of the tile each
 constexpr int TC_OCS = 32 / TC_OPX;              // lanes per pixel = channel splits (4): lane = px + TC_OPX * hf
-static_assert((1 << TC_OPX_SHIFT) == TC_OPX && TC_OPX * TC_OCS == 32 && 8 % TC_OCS == 0, "output-warp lane mapping");
+static_assert((1 << TC_OPX_SHIFT) == TC_OPX && TC_OPX * TC_OCS == 32 && TC_OCS == 2, "output-warp lane mapping: lane = (pixel, quad parity)");
 constexpr int TC_AUX_WARPS = 4;     // TMA producer, MMA issuer, two |z|^2 workers
 constexpr int TC_THREADS = 32 * (TC_AUX_WARPS + TC_SCAN_WARPS + TC_OUT_WARPS);
-constexpr int TC_WLCAP = 32;        // (pixel, code) pairs re-scored exactly per output warp and tile
+constexpr int TC_MAXCAND = 8;       // candidates re-scored exactly per pixel (more: exhaustive fallback)
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_SORT_MAX = 4096;     // codes (16-bit sorted positions, 7-bit chunk indices in the epilogue)
 constexpr int TC_MAX_REP = 32;        // replicas of the per-code sums (spreads the L2 reduction traffic)
@@ -77,7 +77,7 @@ static TcGeom tc_geometry(int D, int K) {
   g.off_aaug = off;  off += 4096;
   g.off_z = off;
   const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16;     // [tile parity][column group][pixel] x 16 B
-  const size_t sz_wl = (size_t)TC_OUT_WARPS * TC_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
+  const size_t sz_wl = 16, sz_zn = 2 * TC_TILE * 4;
   const size_t sz_hist = align_up((size_t)K * 4, 16), sz_perm = align_up(ktot * 2, 16);
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
   const size_t tail = sz_pub + sz_wl + sz_zn + sz_hist + sz_perm + sz_ctab + 256;
@@ -728,7 +728,6 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t emain = sbase + P.off_emain;
     const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
-    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TC_WLCAP * 4);     // this warp's pair list
     const uint32_t zn_s = sbase + P.off_zn;
     const uint32_t perm_a = sbase + P.off_perm;
     float* sums_mine = nullptr;
@@ -813,132 +812,75 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         }
       }
       TC_TICK(2);
-      // ---- pixels with several candidates: (pixel, code) pairs -> exact re-rank ------------------------
-      const int mine = (!fb && total > 1 && hf == 0) ? total : 0;      // pairs this lane contributes
-      int pos = mine;                                                   // inclusive prefix sum over the warp
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, pos, o);
-        if (lane >= o) pos += t;
-      }
-      const int npairs = __shfl_sync(0xffffffffu, pos, 31);
-      pos -= mine;                                                      // exclusive
+      // ---- pixels with several candidates: exact re-rank by the pixel's own two lanes -----------------------
+      // Exact dot product (all kernels of this library): dot = A + B, A / B = ascending-d fma chains over the even /
+      // odd channel quads.  Lane hf of the pixel owns the quads of parity hf, so each lane runs one chain over its own
+      // z values (registers when ZREG) and one shuffle joins the halves; both lanes then take identical decisions.
+      // The warp iterates until its busiest pixel is done (usually two candidates).
+      int rem = (!fb && total > 1) ? total : 0;
+      if (rem > TC_MAXCAND) { fb = true; rem = 0; }      // too many ties: exhaustive search for this pixel
 #ifdef VQ_ABL_NORERANK
-      if (false) {
-#else
-      if (npairs > 0) {
+      rem = 0;
 #endif
-        if (mine > 0) {
-          if (pos + mine > TC_WLCAP) {
-            fb = true;                                    // list full: exhaustive search for this pixel
-          } else {
-            uint32_t wa = wl_s + (uint32_t)pos * 4;
-#pragma unroll
-            for (int i = 0; i < TC_NCG; ++i) {
-#pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                uint32_t m = pw[i][2 + r];
-                const uint32_t base = ((uint32_t)px << 16) | (((pw[i][1] >> (r ? 1 : 8)) & 0x7Fu) * 32u);
-                while (m) {
-                  const int jb = __clz(m);
-                  m &= ~(0x80000000u >> jb);
-                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
-                  wa += 4;
-                }
-              }
-            }
-          }
-        }
-        const uint32_t fbm = __ballot_sync(0xffffffffu, fb && hf == 0);   // the partner lane learns about the overflow
-        fb = ((fbm >> px) & 1u) != 0;
-        // pairs are listed up to the first pixel that did not fit
-        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TC_WLCAP) ? pos : npairs);
-        __syncwarp();
-        unsigned long long key = 0ull;                    // best (score, -original index, position) of my pixel's pairs
-        for (int i0 = 0; i0 < nlist; i0 += 32) {
-          const int i = i0 + lane;
-          const bool act = i < nlist;
-          uint32_t item = 0;                              // idle lanes score (pixel 0, code 0) and drop the result
-          if (act) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
-          const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-          const int pp = ow * TC_OPX + ppx;
+#ifdef VQ_TC_TIMING
+      tacc[7] += __reduce_add_sync(0xffffffffu, (hf == 0) ? rem : 0);
+#endif
+      if (__any_sync(0xffffffffu, rem > 0)) {
+        static_assert(TC_NCG <= 2, "candidate cascade below handles two column groups");
+        uint32_t m0 = pw[0][2], m1 = pw[0][3], m2 = TC_NCG > 1 ? pw[TC_NCG - 1][2] : 0u, m3 = TC_NCG > 1 ? pw[TC_NCG - 1][3] : 0u;
+        const uint32_t c0 = ((pw[0][1] >> 8) & 0x7Fu) * 32u, c1 = ((pw[0][1] >> 1) & 0x7Fu) * 32u;
+        const uint32_t c2 = ((pw[TC_NCG - 1][1] >> 8) & 0x7Fu) * 32u, c3 = ((pw[TC_NCG - 1][1] >> 1) & 0x7Fu) * 32u;
+        unsigned long long key = 0ull;                    // best (score, -original index, position) so far
+        do {
+          // next candidate of my pixel (idle pixels score code 0 and drop the result)
+          const uint32_t mm = m0 ? m0 : m1 ? m1 : m2 ? m2 : m3;
+          const uint32_t cbase = m0 ? c0 : m1 ? c1 : m2 ? c2 : c3;
+          const bool act = rem > 0;
+          const int jb = act ? __clz(mm) : 0;
+          const uint32_t clr = act ? ~(0x80000000u >> jb) : 0xFFFFFFFFu;
+          if (m0) m0 &= clr; else if (m1) m1 &= clr; else if (m2) m2 &= clr; else m3 &= clr;
+          const int k = act ? (int)(cbase + (uint32_t)jb) : 0;
           const int kb = k >> bnsh, row = k & (P.BN - 1);
-          uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
+          const uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128;
           const uint32_t r7 = (uint32_t)(row & 7) << 4;
           float dot = 0.f;
           if (ZREG) {
-            // z(pixel ppx, channel 4j+i) lives in lane ppx + TC_OPX*(j % TC_OCS), register zq[j / TC_OCS][i]
 #pragma unroll
-            for (int j = 0; j < TC_OCS * NZQ; ++j) {
-              const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) << 4) ^ r7));
-              const int src = ppx + TC_OPX * (j % TC_OCS);
-              const float z0 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][0], src);
-              const float z1 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][1], src);
-              const float z2s = __shfl_sync(0xffffffffu, zq[j / TC_OCS][2], src);
-              const float z3 = __shfl_sync(0xffffffffu, zq[j / TC_OCS][3], src);
-              dot = __fmaf_rn(z0, e4.x, dot);
-              dot = __fmaf_rn(z1, e4.y, dot);
-              dot = __fmaf_rn(z2s, e4.z, dot);
-              dot = __fmaf_rn(z3, e4.w, dot);
+            for (int t = 0; t < NZQ; ++t) {
+              const uint32_t j = (uint32_t)(2 * t) + (uint32_t)hf;
+              const float4 e4 = lds_v4(eb + (uint32_t)((2 * t) >> 3) * bn128 + (((j & 7) << 4) ^ r7));
+              dot = __fmaf_rn(zq[t][0], e4.x, dot);
+              dot = __fmaf_rn(zq[t][1], e4.y, dot);
+              dot = __fmaf_rn(zq[t][2], e4.z, dot);
+              dot = __fmaf_rn(zq[t][3], e4.w, dot);
             }
           } else {
-            const uint32_t zr = sbase + P.off_z + zst + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
-            const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
-            const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
-#pragma unroll
-            for (int c = 0; c < nD; ++c) {                  // zero-padded chunks: no guards
-#pragma unroll
-              for (int hb = 0; hb < 2; ++hb) {              // four quads' loads, then their sixteen chained fmas
-                float4 e4[4];
-                float zv[4][4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const int jj = hb * 4 + t;
-                  e4[t] = lds_v4(eb + (((uint32_t)jj << 4) ^ r7));
-                  const uint32_t zo = (uint32_t)c * 16384 + (uint32_t)jj * 512;
-                  zv[t][0] = lds_f32(x0 + zo); zv[t][1] = lds_f32(x1 + zo);
-                  zv[t][2] = lds_f32(x2 + zo); zv[t][3] = lds_f32(x3 + zo);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
-                  dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
-                  dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
-                  dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
-                }
-              }
-              eb += bn128;
+            for (int j = hf; j < nq; j += 2) {
+              const float4 e4 = lds_v4(eb + (uint32_t)(j >> 3) * bn128 + ((((uint32_t)j & 7) << 4) ^ r7));
+              const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+              dot = __fmaf_rn(lds_f32(zj + zx[0]), e4.x, dot);
+              dot = __fmaf_rn(lds_f32(zj + zx[1]), e4.y, dot);
+              dot = __fmaf_rn(lds_f32(zj + zx[2]), e4.z, dot);
+              dot = __fmaf_rn(lds_f32(zj + zx[3]), e4.w, dot);
             }
           }
+          dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 16));     // A + B (commutative: same bits in both lanes)
           uint32_t korig;
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
           // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
           const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
           const float e2k = -2.f * ((au.z + au.y) + au.x);
-          const float z2p = __shfl_sync(0xffffffffu, z2, ppx);           // lane ppx holds |z|^2 of pixel ppx
-          const float sc = ref_score(dot, e2k, z2p);
+          const float sc = ref_score(dot, e2k, z2);
           // ties go to the lowest ORIGINAL index
-          const unsigned long long kcur = !act ? 0ull :
+          const unsigned long long kcur =
               ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - korig) << 16) | (unsigned long long)k;
-          // every pixel lane picks the best of its pairs that were scored in this round (pairs of a pixel are contiguous)
-          const int rel = pos - i0;                       // my first pair, relative to this round
-          const int maxmine = __reduce_max_sync(0xffffffffu, mine);
-          for (int t = 0; t < maxmine; ++t) {
-            const int src = rel + t;
-            const bool take = t < mine && src >= 0 && src < 32;
-            const unsigned long long kk = __shfl_sync(0xffffffffu, kcur, take ? src : 0);
-            if (take && kk > key) key = kk;
-          }
-        }
-        // hand the winner to the partner lanes (hf > 0) of the pixel
-        const unsigned long long kp = __shfl_sync(0xffffffffu, key, px);
-        if (total > 1 && !fb) w = (int)(kp & 0xFFFFull);
+          if (act && kcur > key) key = kcur;
+          rem -= act ? 1 : 0;
+        } while (__any_sync(0xffffffffu, rem > 0));
+        if (!fb && total > 1) w = (int)(key & 0xFFFFull);
       }
 
       TC_TICK(3);
-#ifdef VQ_TC_TIMING
-      tacc[7] += npairs;
-#endif
       // ---- outputs: ids, q, (z-q)^2, EMA statistics ----------------------------------------------------
       const int pp = p0 + p;
       if (fb) {
@@ -1039,7 +981,7 @@ struct TcsGeom {
 };
 constexpr int TCS_MAX_ND = 8;       // D <= 256
 constexpr int TCS_MAX_ES = 4;       // codebook stages
-constexpr int TCS_WLCAP = 64;       // (pixel, code) pairs per output warp and tile (large codebooks tie more often)
+constexpr int TCS_MAXCAND = 16;     // candidates re-scored exactly per pixel (large codebooks tie more often)
 // barrier slots of the streaming kernel
 constexpr int TCS_B_ZFULL = 0, TCS_B_ZEMPTY = 8, TCS_B_EFULL = 16, TCS_B_EEMPTY = 20, TCS_B_AFULL = 24, TCS_B_AEMPTY = 26,
               TCS_B_TFULL = 28, TCS_B_TEMPTY = 30, TCS_B_ZN = 32, TCS_B_PFULL = 34, TCS_B_PEMPTY = 36, TCS_B_TMEM = 38;
@@ -1058,7 +1000,7 @@ static TcsGeom tcs_geometry(int D, int K) {
   g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
   g.off_aaug = off; off += 4096;
   g.off_e = off;
-  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = (size_t)TC_OUT_WARPS * TCS_WLCAP * 4, sz_zn = 2 * TC_TILE * 4;
+  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = 16, sz_zn = 2 * TC_TILE * 4;
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
   const size_t tail = sz_pub + sz_wl + sz_zn + sz_ctab + 512;
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
@@ -1348,7 +1290,6 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
-    const uint32_t wl_s = sbase + P.off_wl + (uint32_t)ow * (TCS_WLCAP * 4);
     const uint32_t zn_s = sbase + P.off_zn;
     float* sums_mine = nullptr;
     if (STATS) {
@@ -1406,94 +1347,56 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
       }
       int worig = __ldg(P.perm + w);
-      // ---- pixels with several candidates: exact fp32 re-rank, code rows from global memory ----------------
-      const int mine = (!fb && total > 1 && hf == 0) ? total : 0;
-      int pos = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, pos, o);
-        if (lane >= o) pos += t;
-      }
-      const int npairs = __shfl_sync(0xffffffffu, pos, 31);
-      pos -= mine;
-      if (npairs > 0) {
-        if (mine > 0) {
-          if (pos + mine > TCS_WLCAP) {
-            fb = true;
-          } else {
-            uint32_t wa = wl_s + (uint32_t)pos * 4;
-#pragma unroll
-            for (int i = 0; i < TC_NCG; ++i) {
-#pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                uint32_t m = pw[i][2 + r];
-                const uint32_t base = ((uint32_t)px << 16) | (((pw[i][1] >> (r ? 1 : 8)) & 0x7Fu) * 32u);
-                while (m) {
-                  const int jb = __clz(m);
-                  m &= ~(0x80000000u >> jb);
-                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(base + (uint32_t)jb) : "memory");
-                  wa += 4;
-                }
-              }
-            }
-          }
-        }
-        const uint32_t fbm = __ballot_sync(0xffffffffu, fb && hf == 0);
-        fb = ((fbm >> px) & 1u) != 0;
-        const int nlist = __reduce_min_sync(0xffffffffu, (mine > 0 && pos + mine > TCS_WLCAP) ? pos : npairs);
-        __syncwarp();
+      // ---- pixels with several candidates: exact fp32 re-rank by the pixel's own two lanes (see the resident kernel);
+      //      code rows from global memory (L2), z from the resident tile ------------------------------------------
+      int rem = (!fb && total > 1) ? total : 0;
+      if (rem > TCS_MAXCAND) { fb = true; rem = 0; }
+      if (__any_sync(0xffffffffu, rem > 0)) {
+        uint32_t m0 = pw[0][2], m1 = pw[0][3], m2 = TC_NCG > 1 ? pw[TC_NCG - 1][2] : 0u, m3 = TC_NCG > 1 ? pw[TC_NCG - 1][3] : 0u;
+        const uint32_t c0 = ((pw[0][1] >> 8) & 0x7Fu) * 32u, c1 = ((pw[0][1] >> 1) & 0x7Fu) * 32u;
+        const uint32_t c2 = ((pw[TC_NCG - 1][1] >> 8) & 0x7Fu) * 32u, c3 = ((pw[TC_NCG - 1][1] >> 1) & 0x7Fu) * 32u;
         unsigned long long key = 0ull;
-        for (int i0 = 0; i0 < nlist; i0 += 32) {
-          const int i = i0 + lane;
-          unsigned long long kcur = 0ull;
-          if (i < nlist) {
-            uint32_t item;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(item) : "r"(wl_s + (uint32_t)i * 4));
-            const int ppx = (int)(item >> 16), k = (int)(item & 0xFFFFu);
-            const int pp = ow * TC_OPX + ppx;
-            const int korig = __ldg(P.perm + k);
-            const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
-            const uint32_t zr = sbase + P.off_z + (uint32_t)(pp >> 5) * 4096 + ((pp & 3) << 2);
-            const uint32_t xs = (uint32_t)((pp & 31) >> 2) << 4;
-            const uint32_t x0 = zr + xs, x1 = zr + 128 + (xs ^ 0x20u), x2 = zr + 256 + (xs ^ 0x40u), x3 = zr + 384 + (xs ^ 0x60u);
-            float dot = 0.f;
-            for (int j0 = 0; j0 < nq; j0 += 4) {          // four quads' loads, then their sixteen chained fmas
-              float4 e4[4];
-              float zv[4][4];
+        do {
+          const uint32_t mm = m0 ? m0 : m1 ? m1 : m2 ? m2 : m3;
+          const uint32_t cbase = m0 ? c0 : m1 ? c1 : m2 ? c2 : c3;
+          const bool act = rem > 0;
+          const int jb = act ? __clz(mm) : 0;
+          const uint32_t clr = act ? ~(0x80000000u >> jb) : 0xFFFFFFFFu;
+          if (m0) m0 &= clr; else if (m1) m1 &= clr; else if (m2) m2 &= clr; else m3 &= clr;
+          const int k = act ? (int)(cbase + (uint32_t)jb) : 0;
+          const int korig = __ldg(P.perm + k);
+          const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
+          float dot = 0.f;
+          for (int j0 = hf; j0 < nq; j0 += 8) {           // four of my quads' loads, then their sixteen chained fmas
+            float4 e4[4];
+            float zv[4][4];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int j = j0 + t;
-                const bool in = j < nq;
-                e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t zo = (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-                zv[t][0] = in ? lds_f32(x0 + zo) : 0.f; zv[t][1] = in ? lds_f32(x1 + zo) : 0.f;
-                zv[t][2] = in ? lds_f32(x2 + zo) : 0.f; zv[t][3] = in ? lds_f32(x3 + zo) : 0.f;
-              }
+            for (int t = 0; t < 4; ++t) {
+              const int j = j0 + 2 * t;
+              const bool in = j < nq;
+              e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
+              zv[t][0] = in ? lds_f32(zj + zx[0]) : 0.f; zv[t][1] = in ? lds_f32(zj + zx[1]) : 0.f;
+              zv[t][2] = in ? lds_f32(zj + zx[2]) : 0.f; zv[t][3] = in ? lds_f32(zj + zx[3]) : 0.f;
+            }
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                if (j0 + t < nq) {
-                  dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
-                  dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
-                  dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
-                  dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
-                }
+            for (int t = 0; t < 4; ++t) {
+              if (j0 + 2 * t < nq) {
+                dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
+                dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
+                dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
+                dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
               }
             }
-            const float sc = ref_score(dot, __ldg(P.e2 + korig), lds_f32(zn_s + (uint32_t)(sl * TC_TILE + pp) * 4));
-            kcur = ((unsigned long long)f32_orderable(sc) << 32) | ((unsigned long long)(0xFFFFu - (uint32_t)korig) << 16) |
-                   (unsigned long long)k;
           }
-          const int rel = pos - i0;
-          const int maxmine = __reduce_max_sync(0xffffffffu, mine);
-          for (int t = 0; t < maxmine; ++t) {
-            const int src = rel + t;
-            const bool take = t < mine && src >= 0 && src < 32;
-            const unsigned long long kk = __shfl_sync(0xffffffffu, kcur, take ? src : 0);
-            if (take && kk > key) key = kk;
-          }
-        }
-        const unsigned long long kp = __shfl_sync(0xffffffffu, key, px);
-        if (total > 1 && !fb) worig = 0xFFFF - (int)((kp >> 16) & 0xFFFFull);
+          dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 16));     // A + B
+          const float sc = ref_score(dot, __ldg(P.e2 + korig), z2);
+          const unsigned long long kcur = ((unsigned long long)f32_orderable(sc) << 32) |
+                                          ((unsigned long long)(0xFFFFu - (uint32_t)korig) << 16) | (unsigned long long)k;
+          if (act && kcur > key) key = kcur;
+          rem -= act ? 1 : 0;
+        } while (__any_sync(0xffffffffu, rem > 0));
+        if (!fb && total > 1) worig = 0xFFFF - (int)((key >> 16) & 0xFFFFull);
       }
 
       // ---- outputs, chunk by chunk; each z chunk goes back to the producer as soon as this warp is done with it ----

@@ -129,6 +129,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // The reference's score for code k and query z (vq_module.py:54-57):
 //   s = fl( fl(2*dot) - |e|^2 ) - |z|^2     (2*dot is exact in binary fp)
+// `dot` is, in every kernel of this library (CUDA-core search, exhaustive fallback, tensor-core re-rank), the same
+// fp32 value: dot = fl(A + B) with A (B) the ascending-d fma chain over the channels whose quad index d >> 2 is even
+// (odd).  Two chains are what the two lanes of a pixel in the tensor-core kernels compute from their own registers;
+// identical summation order everywhere keeps the search paths bit-identical to each other.  |e|^2 and |z|^2 are single
+// ascending-d fma chains.
 __device__ __forceinline__ float ref_score(float dot, float e2, float z2) {
   return __fsub_rn(__fmaf_rn(2.0f, dot, -e2), z2);
 }

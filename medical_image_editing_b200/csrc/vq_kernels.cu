@@ -135,7 +135,7 @@ constexpr int SIMT_DC = 32;    // channel chunk
 
 // One CTA (256 threads) = 128 pixels.  Thread (tx = tid&31, ty = tid>>5) owns pixels 4tx..4tx+3
 // and, in each pass over 64 codes, codes 8ty..8ty+7: a 4x8 register tile of dot products,
-// accumulated over ascending d with one fma chain per (pixel, code).
+// accumulated over ascending d with two fma chains per (pixel, code): even / odd channel quads (exact_dot, vq_common.cuh).
 __global__ void __launch_bounds__(256)
 vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et, const float* __restrict__ e2,
                       const float* __restrict__ E, int B, int D, int H, int W, int K, int Kpad,
@@ -196,11 +196,12 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
     const long long loff = pix_off[li];
 
     for (int cb = 0; cb < Kpad; cb += SIMT_TK) {
-      float acc[4][8];
+      // exact dot product = A + B: one fma chain over the even channel quads, one over the odd ones (vq_common.cuh)
+      float acc[4][8], accB[4][8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+        for (int c = 0; c < 8; ++c) { acc[i][c] = 0.f; accB[i][c] = 0.f; }
 
       for (int d0 = 0; d0 < D; d0 += SIMT_DC) {
         __syncthreads();
@@ -232,17 +233,25 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
             z2[3] = __fmaf_rn(zv.w, zv.w, z2[3]);
           }
         }
-#pragma unroll 4
-        for (int dd = 0; dd < dlim; ++dd) {
-          const float4 zv = *reinterpret_cast<const float4*>(&zs[dd][tx * 4]);
-          const float4 ea = *reinterpret_cast<const float4*>(&es[dd][ty * 8]);
-          const float4 eb = *reinterpret_cast<const float4*>(&es[dd][ty * 8 + 4]);
-          const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-          const float ee[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        for (int d8 = 0; d8 < dlim; d8 += 8) {            // d0 is a multiple of 32: quad parity = (dd >> 2) & 1
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int u = 0; u < 8; ++u) {
+            const int dd = d8 + u;
+            if (dd < dlim) {
+              const float4 zv = *reinterpret_cast<const float4*>(&zs[dd][tx * 4]);
+              const float4 ea = *reinterpret_cast<const float4*>(&es[dd][ty * 8]);
+              const float4 eb = *reinterpret_cast<const float4*>(&es[dd][ty * 8 + 4]);
+              const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+              const float ee[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i][c] = __fmaf_rn(zz[i], ee[c], acc[i][c]);
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  if (u < 4) acc[i][c] = __fmaf_rn(zz[i], ee[c], acc[i][c]);
+                  else accB[i][c] = __fmaf_rn(zz[i], ee[c], accB[i][c]);
+                }
+            }
+          }
         }
       }
       // scores for this block of codes, reference op order; strict '>' keeps the lowest index
@@ -252,7 +261,7 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
         const float ek = e2s[ty * 8 + c];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float s = ref_score(acc[i][c], ek, z2[i]);
+          const float s = ref_score(__fadd_rn(acc[i][c], accB[i][c]), ek, z2[i]);
           if (s > best[i]) { best[i] = s; bidx[i] = k; }
         }
       }
@@ -355,15 +364,27 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
     int bi = 0;
     for (int k0 = 0; k0 < Kpad; k0 += 2 * FB_THREADS) {     // two codes per thread in flight: k, k + 256
       const bool two = k0 + FB_THREADS < Kpad;
-      float acc0 = 0.f, acc1 = 0.f;
+      float acc0 = 0.f, acc1 = 0.f, acc0B = 0.f, acc1B = 0.f;   // dot = A + B (even / odd channel quads, vq_common.cuh)
       const float* ep = et + k0 + tid;
-#pragma unroll 8
-      for (int d = 0; d < D; ++d) {
-        const float zv = zr[d];
-        const float* row = ep + (size_t)d * Kpad;
-        acc0 = __fmaf_rn(zv, __ldg(row), acc0);
-        if (two) acc1 = __fmaf_rn(zv, __ldg(row + FB_THREADS), acc1);
+      for (int d8 = 0; d8 < D; d8 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int d = d8 + u;
+          if (d < D) {
+            const float zv = zr[d];
+            const float* row = ep + (size_t)d * Kpad;
+            if (u < 4) {
+              acc0 = __fmaf_rn(zv, __ldg(row), acc0);
+              if (two) acc1 = __fmaf_rn(zv, __ldg(row + FB_THREADS), acc1);
+            } else {
+              acc0B = __fmaf_rn(zv, __ldg(row), acc0B);
+              if (two) acc1B = __fmaf_rn(zv, __ldg(row + FB_THREADS), acc1B);
+            }
+          }
+        }
       }
+      acc0 = __fadd_rn(acc0, acc0B);
+      acc1 = __fadd_rn(acc1, acc1B);
       {                                                      // ascending k per thread, strict '>' keeps the lowest index
         const int k = k0 + tid;
         const float sc = ref_score(acc0, __ldg(e2 + k), z2);
