@@ -321,7 +321,10 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
       pos = rank;
       const float r = __uint_as_float(mine);
       if (r <= rcap) {
-        const float x = -0.5f * e2[i];
+        // tf32 operands are TRUNCATED (tools/trunc_check.py), so every product shrinks by a factor in (1 - 2^-9, 1]:
+        // (1 + 2^-10) * dot~ is within 2^-10 sum|z_d e_d| of the exact dot -- half of the uncentred bound.  Comparing
+        // (1 + 2^-10) dot~ - |e|^2/2 is comparing dot~ - |e|^2 / (2 (1 + 2^-10)): fold the factor into the augmentation.
+        const float x = -0.5f * e2[i] * (1.0f / (1.0f + 0.0009765625f));
         a0 = tf32_trunc(x);
         const float r1 = x - a0;
         a1 = tf32_trunc(r1);
@@ -334,7 +337,7 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
     perm[pos] = real ? i : 0;
     const int blk = pos / BN, rr = pos % BN, grp = rr >> 3, row = rr & 7;
     float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
-    base[0] = a0; base[1] = a1; base[2] = a2; base[3] = 0.f;
+    base[0] = a0; base[1] = a1; base[2] = a2; base[3] = real ? e2[i] : 0.f;   // [3]: exact |e|^2 (times the zero row of the ones block)
     base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
     // sorted copy of the codebook row (TMA source)
     const int dq = D >> 2;
@@ -468,7 +471,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
     for (int k = t; k < P.K; k += NT) hist[k] = 0;
     for (int k = t; k < ktot; k += NT) perm_s[k] = (uint16_t)P.perm[k];
     {   // per-chunk error-bound coefficients from the chunk's largest norm (already includes the rounding slop)
-      const float c1 = 0.00390625f * 1.03f;                     // 2^-8: z and e both truncated to tf32 (score units)
+      const float c1 = 0.001953125f * 1.03f;                    // 2^-9 (score units): truncated tf32 operands, centred (prep2)
       const float c2 = (float)(Dc + 16) * 4.76837158e-7f;       // (D+16) 2^-21: fp32 accumulation in the tensor core
       for (int c = t; c < P.nb * (P.BN >> 5); c += NT) {
         const float rm = __uint_as_float(P.rmax[c]);
@@ -795,7 +798,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
         else ovf |= (pw[i][1] & 1u) != 0;
         total += __popc(pw[i][2]) + __popc(pw[i][3]);
       }
-      const float lbest = 2.f * Lg;                       // lower bound on the best exact score 2 a_k (before -|z|^2)
+      const float lbest = 2.f * (Lg < 0.f ? Lg * 1.0009765625f : Lg);   // lower bound on the best exact 2 a_k (accumulators are a_k / (1 + 2^-10))
       // excluded ("big") codes: s_k <= r_k (2|z| - r_k), decreasing in r_k for r_k >= |z|
       bool big_safe = true;
       if (rminbig < 3.0e38f) {
@@ -867,9 +870,9 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
           dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, 16));     // A + B (commutative: same bits in both lanes)
           uint32_t korig;
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
-          // |e|^2 from the augmentation image: a0 + a1 + a2 == -|e|^2/2 exactly (three 11-bit pieces of 24 bits)
+          // exact |e|^2: fourth float of the code's augmentation entry (it meets the zero row of the ones block in the MMA)
           const float4 au = lds_v4(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16));
-          const float e2k = -2.f * ((au.z + au.y) + au.x);
+          const float e2k = au.w;
           const float sc = ref_score(dot, e2k, z2);
           // ties go to the lowest ORIGINAL index
           const unsigned long long kcur =
@@ -970,21 +973,23 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // streaming variant: codebooks that do not fit in shared memory (K*D*4 > ~140 KB, e.g. K=512 x D=256, K=4096 x D=64)
 // ---------------------------------------------------------------------------------------------
-// The z tile (128 pixels x D) stays resident as a ring of 32-channel chunks; the norm-sorted codebook streams through
-// a ring of [BN codes x 32 channels] stages (classic K-loop pipelining, one tcgen05.commit per stage).  Scan and merge
-// are the same as in the resident kernel; the output warps read the exact fp32 code rows from global memory (L2) and
-// hand the z chunks back to the producer one by one, so the next tile's z streams in while this tile is written out.
+// Nothing is resident: one ring of stages, each stage = one 32-channel chunk of the z tile (128 pixels x 128 B) plus the
+// matching [BN codes x 32 channels] slice of the norm-sorted codebook (classic K-loop pipelining, one tcgen05.commit per
+// stage).  The z tile is streamed once per code block (it comes out of L2 after the first pass), so all of the shared
+// memory holds bytes in flight -- with a resident z tile (128 KB at D = 256) only two codebook stages fitted and the
+// kernel was bound by TMA latency.  Scan and merge are the same as in the resident kernel; the output warps read z and
+// the exact fp32 code rows from global memory (both L2 hits: the tile and the codebook were just streamed).
 struct TcsGeom {
-  int BN, nb, nD, nes;
-  size_t off_z, off_e, off_aug, off_aaug, off_pub, off_wl, off_zn, off_ctab, off_bar, total;
+  int BN, nb, nD, nst;
+  size_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_pz, off_zn, off_ctab, off_bar, total;
   bool ok;
 };
 constexpr int TCS_MAX_ND = 8;       // D <= 256
-constexpr int TCS_MAX_ES = 4;       // codebook stages
+constexpr int TCS_MAX_ST = 8;       // ring stages
 constexpr int TCS_MAXCAND = 16;     // candidates re-scored exactly per pixel (large codebooks tie more often)
 // barrier slots of the streaming kernel
-constexpr int TCS_B_ZFULL = 0, TCS_B_ZEMPTY = 8, TCS_B_EFULL = 16, TCS_B_EEMPTY = 20, TCS_B_AFULL = 24, TCS_B_AEMPTY = 26,
-              TCS_B_TFULL = 28, TCS_B_TEMPTY = 30, TCS_B_ZN = 32, TCS_B_PFULL = 34, TCS_B_PEMPTY = 36, TCS_B_TMEM = 38;
+constexpr int TCS_B_FULL = 0, TCS_B_EMPTY = 8, TCS_B_AFULL = 16, TCS_B_AEMPTY = 18, TCS_B_TFULL = 20, TCS_B_TEMPTY = 22,
+              TCS_B_ZN = 24, TCS_B_PFULL = 26, TCS_B_PEMPTY = 28, TCS_B_TMEM = 30;
 
 static TcsGeom tcs_geometry(int D, int K) {
   TcsGeom g{};
@@ -994,23 +999,22 @@ static TcsGeom tcs_geometry(int D, int K) {
   g.nb = (K + g.BN - 1) / g.BN;
   g.nD = (D + TC_DCH - 1) / TC_DCH;
   if (g.nD > TCS_MAX_ND || g.nb * g.BN > TC_SORT_MAX) return g;
-  const size_t estage = (size_t)g.BN * 128;
+  g.stage_bytes = (size_t)TC_TILE * 128 + (size_t)g.BN * 128;          // z chunk + codebook slice (both 1024-aligned)
   size_t off = 0;
-  g.off_z = off;    off += (size_t)g.nD * TC_TILE * 128;
   g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
   g.off_aaug = off; off += 4096;
-  g.off_e = off;
-  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_wl = 16, sz_zn = 2 * TC_TILE * 4;
+  g.off_stage = off;
+  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_zn = 2 * TC_TILE * 4;
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
-  const size_t tail = sz_pub + sz_wl + sz_zn + sz_ctab + 512;
+  const size_t tail = sz_pub + 2 * sz_zn + sz_ctab + 512;
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
-  int nes = (int)(room / (long long)estage);
-  if (nes > TCS_MAX_ES) nes = TCS_MAX_ES;
-  if (nes < 2) return g;
-  g.nes = nes;
-  off += (size_t)nes * estage;
+  int nst = (int)(room / (long long)g.stage_bytes);
+  if (nst > TCS_MAX_ST) nst = TCS_MAX_ST;
+  if (nst < 2) return g;
+  g.nst = nst;
+  off += (size_t)nst * g.stage_bytes;
   g.off_pub = off;  off += sz_pub;
-  g.off_wl = off;   off += sz_wl;
+  g.off_pz = off;   off += sz_zn;      // |z|^2 forwarded by the scan warps together with their results
   g.off_zn = off;   off += sz_zn;
   g.off_ctab = off; off += sz_ctab;
   g.off_bar = off;  off += 512;
@@ -1023,10 +1027,10 @@ struct TcsParams {
   const float* z; const float* E; const float* e2; const float* eaug_img; const uint32_t* meta;
   const int* perm; const uint32_t* rmax;
   int B, D, H, W, HW, K;
-  int BN, nb, nD, nes;
+  int BN, nb, nD, nst;
   int bn_shift, w_shift;
   int tiles_per_img; int ntiles;
-  uint32_t off_z, off_e, off_aug, off_aaug, off_pub, off_wl, off_zn, off_ctab, off_bar;
+  uint32_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_pz, off_zn, off_ctab, off_bar;
   int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
   float* sums; float* sums_rep; int nrep;
   int* fb_count; int* fb_rows;
@@ -1044,13 +1048,12 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
   const uint32_t bar0 = sbase + P.off_bar;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(bars + TCS_B_TMEM);
-  const int nD = P.nD, nes = P.nes;
+  const int nD = P.nD, nst = P.nst;
   const int ktot = P.nb * P.BN;
-  const uint32_t estage = (uint32_t)P.BN * 128;
+  const uint32_t stage_bytes = P.stage_bytes;                 // z chunk (16 KB) followed by the codebook slice
 
   if (threadIdx.x == 32) {
-    for (int c = 0; c < TCS_MAX_ND; ++c) { mbar_init(BAR(TCS_B_ZFULL + c), 1); mbar_init(BAR(TCS_B_ZEMPTY + c), TC_OUT_WARPS + 3); }
-    for (int e = 0; e < TCS_MAX_ES; ++e) { mbar_init(BAR(TCS_B_EFULL + e), 1); mbar_init(BAR(TCS_B_EEMPTY + e), 1); }
+    for (int i = 0; i < TCS_MAX_ST; ++i) { mbar_init(BAR(TCS_B_FULL + i), 1); mbar_init(BAR(TCS_B_EMPTY + i), 3); }   // MMA commit + |z|^2 warps
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(TCS_B_AFULL + i), 1); mbar_init(BAR(TCS_B_AEMPTY + i), 1);
       mbar_init(BAR(TCS_B_TFULL + i), 1); mbar_init(BAR(TCS_B_TEMPTY + i), TC_SCAN_WARPS);
@@ -1072,7 +1075,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       const float v = row < 3 ? 1.f : 0.f;
       a[i] = make_float4(v, v, v, v);
     }
-    const float c1 = 0.00390625f * 1.03f;
+    const float c1 = 0.001953125f * 1.03f;                      // see the resident kernel
     const float c2 = (float)(P.D + 16) * 4.76837158e-7f;
     for (int c = t; c < P.nb * (P.BN >> 5); c += NT) {
       const float rm = __uint_as_float(P.rmax[c]);
@@ -1090,7 +1093,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      int ecount = 0, acount = 0;
+      int scount = 0, acount = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
@@ -1103,19 +1106,14 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
                          BAR(TCS_B_AFULL + as));
             ++acount;
           }
-          for (int c = 0; c < nD; ++c) {
-            if (blk == 0) {                                // the z chunk of this tile (freed by the previous tile's readers)
-              mbar_wait_sleep(BAR(TCS_B_ZEMPTY + c), (it & 1) ^ 1, 64);
-              mbar_expect_tx(BAR(TCS_B_ZFULL + c), TC_TILE * 128);
-              for (int grp = 0; grp < 4; ++grp)
-                tma_load_3d(sbase + P.off_z + c * (TC_TILE * 128) + grp * 4096, &zmap, BAR(TCS_B_ZFULL + c),
-                            pt * TC_TILE + grp * 32, c * TC_DCH, b);
-            }
-            const int es = ecount % nes;
-            mbar_wait_sleep(BAR(TCS_B_EEMPTY + es), ((ecount / nes) & 1) ^ 1, 32);
-            mbar_expect_tx(BAR(TCS_B_EFULL + es), estage);
-            tma_load_2d(sbase + P.off_e + (uint32_t)es * estage, &emap, BAR(TCS_B_EFULL + es), c * TC_DCH, blk * P.BN);
-            ++ecount;
+          for (int c = 0; c < nD; ++c, ++scount) {
+            const int st = scount % nst;
+            mbar_wait_sleep(BAR(TCS_B_EMPTY + st), ((scount / nst) & 1) ^ 1, 32);
+            mbar_expect_tx(BAR(TCS_B_FULL + st), stage_bytes);
+            const uint32_t dst = sbase + P.off_stage + (uint32_t)st * stage_bytes;
+            for (int grp = 0; grp < 4; ++grp)             // z chunk: four 32-pixel x 32-channel boxes
+              tma_load_3d(dst + grp * 4096, &zmap, BAR(TCS_B_FULL + st), pt * TC_TILE + grp * 32, c * TC_DCH, b);
+            tma_load_2d(dst + TC_TILE * 128, &emap, BAR(TCS_B_FULL + st), c * TC_DCH, blk * P.BN);
           }
         }
       }
@@ -1124,7 +1122,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(P.BN);
-      int g = 0, ecount = 0, acount = 0;
+      int g = 0, scount = 0, acount = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int blk = 0; blk < P.nb; ++blk, ++g) {
           const int a = g & 1, aph = (g >> 1) & 1;
@@ -1132,23 +1130,20 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
           uint32_t acc = 0;
-          for (int c = 0; c < nD; ++c) {
-            if (blk == 0) mbar_wait_sleep(BAR(TCS_B_ZFULL + c), it & 1, 32);
-            const int es = ecount % nes;
-            mbar_wait_sleep(BAR(TCS_B_EFULL + es), (ecount / nes) & 1, 32);
+          for (int c = 0; c < nD; ++c, ++scount) {
+            const int st = scount % nst;
+            mbar_wait_sleep(BAR(TCS_B_FULL + st), (scount / nst) & 1, 32);
             tc_fence_after();
             const int ksteps = min(4, (P.D - c * TC_DCH + 7) >> 3);
-            const uint32_t zaddr = sbase + P.off_z + c * (TC_TILE * 128);
-            const uint32_t eaddr = sbase + P.off_e + (uint32_t)es * estage;
+            const uint32_t zaddr = sbase + P.off_stage + (uint32_t)st * stage_bytes;
+            const uint32_t eaddr = zaddr + TC_TILE * 128;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t ad = make_desc(zaddr + ks * 1024, 4096, 512, 1);
               const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
               umma_tf32(d_tmem, ad, bd, idesc, acc);
               acc = 1;
             }
-            umma_commit(BAR(TCS_B_EEMPTY + es));           // codebook stage consumed
-            ++ecount;
-            if (blk == P.nb - 1) umma_commit(BAR(TCS_B_ZEMPTY + c));   // last use of this z chunk by the tensor core
+            umma_commit(BAR(TCS_B_EMPTY + st));            // stage consumed by the tensor core
           }
           {
             const int as = acount & 1;
@@ -1166,32 +1161,43 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     }
   } else if (warp < TC_AUX_WARPS) {
     // ===================================== |z|^2 workers ====================================
+    // read the z chunks of the first code block's pass; the later passes of the tile only hand the stage back
     const int pA = (warp - 2) * 64 + 2 * lane;
-    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
+    const uint32_t zrow0 = sbase + P.off_stage + (uint32_t)(pA >> 5) * 4096 + ((pA & 3) << 2);
     const uint32_t zn_s = sbase + P.off_zn;
     uint32_t zx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((pA & 31) >> 2) ^ (i << 1)) << 4);
+    int scount = 0;
     for (int it = 0; it < my_tiles; ++it) {
       float2 zz = make_float2(0.f, 0.f);
-      for (int c = 0; c < nD; ++c) {
-        mbar_wait(BAR(TCS_B_ZFULL + c), it & 1);
-        const uint32_t zc = zrow0 + (uint32_t)c * 16384;
+      for (int blk = 0; blk < P.nb; ++blk) {
+        for (int c = 0; c < nD; ++c, ++scount) {
+          const int st = scount % nst;
+          // always wait for the fill: an arrival may only count for the phase it belongs to (the producer refills a
+          // stage after the previous phase of its EMPTY barrier completed)
+          mbar_wait(BAR(TCS_B_FULL + st), (scount / nst) & 1);
+          if (blk == 0) {
+            const uint32_t zc = zrow0 + (uint32_t)st * stage_bytes;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+            for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 v = lds_v2(zc + jj * 512 + zx[i]);
-            zz = __ffma2_rn(v, v, zz);
+              for (int i = 0; i < 4; ++i) {
+                const float2 v = lds_v2(zc + jj * 512 + zx[i]);
+                zz = __ffma2_rn(v, v, zz);
+              }
+            }
+            __syncwarp();
           }
+          if (lane == 0) mbar_arrive(BAR(TCS_B_EMPTY + st));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(TCS_B_ZEMPTY + c));
+        if (blk == 0) {
+          const int sl = it & 1;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(zn_s + (uint32_t)(sl * TC_TILE + pA) * 4), "f"(zz.x), "f"(zz.y) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(TCS_B_ZN + sl));
+        }
       }
-      const int sl = it & 1;
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(zn_s + (uint32_t)(sl * TC_TILE + pA) * 4), "f"(zz.x), "f"(zz.y) : "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(TCS_B_ZN + sl));
     }
   } else if (warp < TC_AUX_WARPS + TC_SCAN_WARPS) {
     // ===================================== scan warps (as in the resident kernel) ==========================
@@ -1203,9 +1209,12 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     const int nchunks = P.BN >> 5;
     int g = 0;
     int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // only for the debug dump
+    TC_TIMING_DECL
     for (int it = 0; it < my_tiles; ++it) {
       const int sl = it & 1, sph = (it >> 1) & 1;
+      TC_TICK(4);
       mbar_wait(BAR(TCS_B_ZN + sl), sph);
+      TC_TICK(0);
       float z2;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)sl * (TC_TILE * 4)));
       const float zn = sqrtf(z2) * 1.00001f;
@@ -1214,7 +1223,9 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       uint32_t rcA = 0, rcB = 0, rm0 = 0, rm1 = 0;
       for (int blk = 0; blk < P.nb; ++blk, ++g) {
         const int a = g & 1, aph = (g >> 1) & 1;
+        TC_TICK(2);
         mbar_wait(BAR(TCS_B_TFULL + a), aph);
+        TC_TICK(1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN;
         for (int c = cg; c < nchunks; c += TC_NCG) {
@@ -1272,25 +1283,28 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       if (cnt < 1) rm0 = 0;
       const uint32_t w1 = f32_up16(Urec) | (rcA << 8) | (rcB << 1) | (cnt > 2 ? 1u : 0u);
       const int par = it & 1, pph = (it >> 1) & 1;
+      TC_TICK(2);
       mbar_wait(BAR(TCS_B_PEMPTY + par), pph ^ 1);
+      TC_TICK(3);
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_s + (uint32_t)par * (TC_NCG * TC_TILE * 16)),
                    "r"(__float_as_uint(L)), "r"(w1), "r"(rm0), "r"(rm1) : "memory");
+      // the |z|^2 slot may be rewritten (tile it+2) before the output warps get to this tile: forward it with the results
+      if (cg == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbase + P.off_pz + (uint32_t)(par * TC_TILE + p) * 4), "f"(z2) : "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(TCS_B_PFULL + par));
     }
+    TC_TIMING_STORE(warp - TC_AUX_WARPS, my_tiles);
   } else {
     // ===================================== output warps =====================================
+    // Same decisions as in the resident kernel (lane = pixel x quad parity); z and the exact fp32 code rows come from
+    // global memory (L2 hits: the tile and the codebook were just streamed), so these warps never touch the ring.
     const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
     const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
     const int p = ow * TC_OPX + px;
     const float rminbig = __uint_as_float(P.meta[1]);
     const int D = P.D, nq = D >> 2;
-    const uint32_t zrow = sbase + P.off_z + (uint32_t)(p >> 5) * 4096 + ((p & 3) << 2);
-    uint32_t zx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)((((p & 31) >> 2) ^ (i << 1)) << 4);
     const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
-    const uint32_t zn_s = sbase + P.off_zn;
+    const uint32_t pz_s = sbase + P.off_pz + (uint32_t)p * 4;
     float* sums_mine = nullptr;
     if (STATS) {
       const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
@@ -1300,16 +1314,19 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     const size_t img_stride = (size_t)D * hw;
     float2 ls2 = make_float2(0.f, 0.f);
     int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;
+    TC_TIMING_DECL
     for (int it = 0; it < my_tiles; ++it) {
       const int sl = it & 1, sph = (it >> 1) & 1;
       const int b = tb, p0 = tpt * TC_TILE;
       tpt += (int)gridDim.x;
       while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
-      for (int c = 0; c < nD; ++c) mbar_wait(BAR(TCS_B_ZFULL + c), it & 1);   // z chunks visible to this thread
-      mbar_wait(BAR(TCS_B_ZN + sl), sph);
-      float z2;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)(sl * TC_TILE + p) * 4));
+      const int pp = p0 + p;
+      const float* zp = P.z + (size_t)b * img_stride + pp;           // z(pixel, channel d) = zp[d * hw]
+      TC_TICK(4);
       mbar_wait(BAR(TCS_B_PFULL + sl), sph);
+      TC_TICK(1);
+      float z2;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(pz_s + (uint32_t)sl * (TC_TILE * 4)));
       const float zn = sqrtf(z2) * 1.00001f;
       const bool bad = !(z2 <= 3.0e38f);
       uint32_t pw[TC_NCG][4];
@@ -1331,7 +1348,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         else ovf |= (pw[i][1] & 1u) != 0;
         total += __popc(pw[i][2]) + __popc(pw[i][3]);
       }
-      const float lbest = 2.f * Lg;
+      const float lbest = 2.f * (Lg < 0.f ? Lg * 1.0009765625f : Lg);
       bool big_safe = true;
       if (rminbig < 3.0e38f) {
         const float bigub = rminbig * (2.f * zn - rminbig);
@@ -1347,8 +1364,10 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
       }
       int worig = __ldg(P.perm + w);
-      // ---- pixels with several candidates: exact fp32 re-rank by the pixel's own two lanes (see the resident kernel);
-      //      code rows from global memory (L2), z from the resident tile ------------------------------------------
+      TC_TICK(2);
+      // ---- pixels with several candidates: exact fp32 re-rank by the pixel's own two lanes (see the resident kernel) ----
+      // (a variant with the whole warp on one (pixel, code) pair and the fma chains travelling from lane to lane was
+      //  slower: at D = 256 a warp has 3-4 such pixels per tile and they are better served in parallel)
       int rem = (!fb && total > 1) ? total : 0;
       if (rem > TCS_MAXCAND) { fb = true; rem = 0; }
       if (__any_sync(0xffffffffu, rem > 0)) {
@@ -1365,27 +1384,29 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           if (m0) m0 &= clr; else if (m1) m1 &= clr; else if (m2) m2 &= clr; else m3 &= clr;
           const int k = act ? (int)(cbase + (uint32_t)jb) : 0;
           const int korig = __ldg(P.perm + k);
-          const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
           float dot = 0.f;
-          for (int j0 = hf; j0 < nq; j0 += 8) {           // four of my quads' loads, then their sixteen chained fmas
-            float4 e4[4];
-            float zv[4][4];
+          if (act) {                                      // divergent on purpose: idle pixels issue no loads
+            const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)korig * D);
+            for (int j0 = hf; j0 < nq; j0 += 8) {         // four of my quads' loads, then their sixteen chained fmas
+              float4 e4[4];
+              float zv[4][4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int j = j0 + 2 * t;
-              const bool in = j < nq;
-              e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const uint32_t zj = zrow + (uint32_t)(j >> 3) * 16384 + (uint32_t)(j & 7) * 512;
-              zv[t][0] = in ? lds_f32(zj + zx[0]) : 0.f; zv[t][1] = in ? lds_f32(zj + zx[1]) : 0.f;
-              zv[t][2] = in ? lds_f32(zj + zx[2]) : 0.f; zv[t][3] = in ? lds_f32(zj + zx[3]) : 0.f;
-            }
+              for (int t = 0; t < 4; ++t) {
+                const int j = j0 + 2 * t;
+                const bool in = j < nq;
+                e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* zj = zp + (size_t)(4 * j) * hw;
+                zv[t][0] = in ? __ldg(zj) : 0.f;          zv[t][1] = in ? __ldg(zj + hw) : 0.f;
+                zv[t][2] = in ? __ldg(zj + 2 * hw) : 0.f; zv[t][3] = in ? __ldg(zj + 3 * hw) : 0.f;
+              }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              if (j0 + 2 * t < nq) {
-                dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
-                dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
-                dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
-                dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
+              for (int t = 0; t < 4; ++t) {
+                if (j0 + 2 * t < nq) {
+                  dot = __fmaf_rn(zv[t][0], e4[t].x, dot);
+                  dot = __fmaf_rn(zv[t][1], e4[t].y, dot);
+                  dot = __fmaf_rn(zv[t][2], e4[t].z, dot);
+                  dot = __fmaf_rn(zv[t][3], e4[t].w, dot);
+                }
               }
             }
           }
@@ -1399,42 +1420,45 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         if (!fb && total > 1) worig = 0xFFFF - (int)((key >> 16) & 0xFFFFull);
       }
 
-      // ---- outputs, chunk by chunk; each z chunk goes back to the producer as soon as this warp is done with it ----
-      const int pp = p0 + p;
+      TC_TICK(3);
+      // ---- outputs ------------------------------------------------------------------------------------
       if (fb) {
         if (hf == 0) {
           const int slot = atomicAdd(P.fb_count, 1);
           P.fb_rows[slot] = b * P.HW + pp;
         }
-      } else if (hf == 0) {
-        int h, wc;
-        if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
-        else { h = pp / P.W; wc = pp - h * P.W; }
-        const size_t nb_ = (size_t)b * hw;
-        if (P.ids) P.ids[nb_ + (size_t)(wc * P.H + h)] = (int64_t)worig;
-        if (P.ids_nat) P.ids_nat[nb_ + pp] = worig;
-        if (STATS) atomicAdd(&P.counts[worig], 1);
-      }
-      const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)worig * D);
-      float* qo = P.q + (size_t)b * img_stride + pp;
-      float* so = STATS ? sums_mine + (size_t)worig * D : nullptr;
-      for (int c = 0; c < nD; ++c) {
-        if (!fb) {
-          float4 e4[8 / TC_OCS];
+      } else {
+        if (hf == 0) {
+          int h, wc;
+          if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
+          else { h = pp / P.W; wc = pp - h * P.W; }
+          const size_t nb_ = (size_t)b * hw;
+          if (P.ids) P.ids[nb_ + (size_t)(wc * P.H + h)] = (int64_t)worig;
+          if (P.ids_nat) P.ids_nat[nb_ + pp] = worig;
+          if (STATS) atomicAdd(&P.counts[worig], 1);
+        }
+        const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)worig * D);
+        float* qo = P.q + (size_t)b * img_stride + pp;
+        float* so = STATS ? sums_mine + (size_t)worig * D : nullptr;
+        for (int j0 = hf; j0 < nq; j0 += 8) {             // my quads j = j0 + 2t: all loads of four quads first
+          float4 e4[4];
+          float zv[4][4];
 #pragma unroll
-          for (int t = 0; t < 8 / TC_OCS; ++t) {          // quads j = 8c + TC_OCS*t + hf of this chunk
-            const int j = 8 * c + TC_OCS * t + hf;
-            e4[t] = j < nq ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < 4; ++t) {
+            const int j = j0 + 2 * t;
+            const bool in = j < nq;
+            e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* zj = zp + (size_t)(4 * j) * hw;
+            zv[t][0] = in ? __ldg(zj) : 0.f;          zv[t][1] = in ? __ldg(zj + hw) : 0.f;
+            zv[t][2] = in ? __ldg(zj + 2 * hw) : 0.f; zv[t][3] = in ? __ldg(zj + 3 * hw) : 0.f;
           }
 #pragma unroll
-          for (int t = 0; t < 8 / TC_OCS; ++t) {
-            const int j = 8 * c + TC_OCS * t + hf;
+          for (int t = 0; t < 4; ++t) {
+            const int j = j0 + 2 * t;
             if (j < nq) {
-              const uint32_t zj = zrow + (uint32_t)c * 16384 + (uint32_t)(TC_OCS * t + hf) * 512;
-              const float z0 = lds_f32(zj + zx[0]), z1 = lds_f32(zj + zx[1]), z2v = lds_f32(zj + zx[2]), z3 = lds_f32(zj + zx[3]);
               const float2 m1 = make_float2(-1.f, -1.f);
-              const float2 d01 = __ffma2_rn(make_float2(e4[t].x, e4[t].y), m1, make_float2(z0, z1));
-              const float2 d23 = __ffma2_rn(make_float2(e4[t].z, e4[t].w), m1, make_float2(z2v, z3));
+              const float2 d01 = __ffma2_rn(make_float2(e4[t].x, e4[t].y), m1, make_float2(zv[t][0], zv[t][1]));
+              const float2 d23 = __ffma2_rn(make_float2(e4[t].z, e4[t].w), m1, make_float2(zv[t][2], zv[t][3]));
               ls2 = __ffma2_rn(d01, d01, ls2);
               ls2 = __ffma2_rn(d23, d23, ls2);
               if (!DBG || P.q) {
@@ -1444,14 +1468,14 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
                 __stcs(qj + 2 * hw, e4[t].z);
                 __stcs(qj + 3 * hw, e4[t].w);
               }
-              if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(z0, z1, z2v, z3));
+              if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(zv[t][0], zv[t][1], zv[t][2], zv[t][3]));
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(TCS_B_ZEMPTY + c));
       }
     }
+    TC_TICK(4);
+    TC_TIMING_STORE(8 + ow, my_tiles);
     float lsum = ls2.x + ls2.y;
     lsum = warp_sum(lsum);
     if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
@@ -1629,15 +1653,16 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
   P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
   P.perm = a.ws.tc_perm; P.rmax = rmax;
   P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
-  P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nes = g.nes;
+  P.BN = g.BN; P.nb = g.nb; P.nD = g.nD; P.nst = g.nst;
   P.bn_shift = 0;
   while ((1 << P.bn_shift) < g.BN) ++P.bn_shift;
   P.w_shift = -1;
   if ((a.W & (a.W - 1)) == 0) { P.w_shift = 0; while ((1 << P.w_shift) < a.W) ++P.w_shift; }
   P.tiles_per_img = HW / TC_TILE;
   P.ntiles = a.B * P.tiles_per_img;
-  P.off_z = (uint32_t)g.off_z; P.off_e = (uint32_t)g.off_e; P.off_aug = (uint32_t)g.off_aug; P.off_aaug = (uint32_t)g.off_aaug;
-  P.off_pub = (uint32_t)g.off_pub; P.off_wl = (uint32_t)g.off_wl; P.off_zn = (uint32_t)g.off_zn;
+  P.stage_bytes = (uint32_t)g.stage_bytes; P.off_stage = (uint32_t)g.off_stage;
+  P.off_aug = (uint32_t)g.off_aug; P.off_aaug = (uint32_t)g.off_aaug;
+  P.off_pub = (uint32_t)g.off_pub; P.off_pz = (uint32_t)g.off_pz; P.off_zn = (uint32_t)g.off_zn;
   P.off_ctab = (uint32_t)g.off_ctab; P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
   P.counts = a.stats ? a.ws.counts : nullptr;
