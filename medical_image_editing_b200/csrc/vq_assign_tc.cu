@@ -981,7 +981,7 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 // the exact fp32 code rows from global memory (both L2 hits: the tile and the codebook were just streamed).
 struct TcsGeom {
   int BN, nb, nD, nst;
-  size_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_pz, off_zn, off_ctab, off_bar, total;
+  size_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_bar, total;
   bool ok;
 };
 constexpr int TCS_MAX_ND = 8;       // D <= 256
@@ -989,7 +989,7 @@ constexpr int TCS_MAX_ST = 8;       // ring stages
 constexpr int TCS_MAXCAND = 16;     // candidates re-scored exactly per pixel (large codebooks tie more often)
 // barrier slots of the streaming kernel
 constexpr int TCS_B_FULL = 0, TCS_B_EMPTY = 8, TCS_B_AFULL = 16, TCS_B_AEMPTY = 18, TCS_B_TFULL = 20, TCS_B_TEMPTY = 22,
-              TCS_B_ZN = 24, TCS_B_PFULL = 26, TCS_B_PEMPTY = 28, TCS_B_TMEM = 30;
+              TCS_B_ZN = 24, TCS_B_TMEM = 30;
 
 static TcsGeom tcs_geometry(int D, int K) {
   TcsGeom g{};
@@ -1004,17 +1004,19 @@ static TcsGeom tcs_geometry(int D, int K) {
   g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
   g.off_aaug = off; off += 4096;
   g.off_stage = off;
-  const size_t sz_pub = (size_t)2 * TC_NCG * TC_TILE * 16, sz_zn = 2 * TC_TILE * 4;
+  const size_t sz_pub = (size_t)4 * TC_NCG * TC_TILE * 16, sz_zn = 2 * TC_TILE * 4;   // pub: [team][tile parity][column group][pixel]
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
-  const size_t tail = sz_pub + 2 * sz_zn + sz_ctab + 512;
+  const size_t tail = sz_pub + sz_zn + sz_ctab + 512;
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
   int nst = (int)(room / (long long)g.stage_bytes);
   if (nst > TCS_MAX_ST) nst = TCS_MAX_ST;
+  // the |z|^2 slot of tile it is rewritten for tile it+2: the producer must not run that far ahead of the tensor core
+  // (its first block of tile it+1 starts only after the team has read the slot) -- see the epilogue warps
+  if (nst > (g.nb + 1) * g.nD - 1) nst = (g.nb + 1) * g.nD - 1;
   if (nst < 2) return g;
   g.nst = nst;
   off += (size_t)nst * g.stage_bytes;
   g.off_pub = off;  off += sz_pub;
-  g.off_pz = off;   off += sz_zn;      // |z|^2 forwarded by the scan warps together with their results
   g.off_zn = off;   off += sz_zn;
   g.off_ctab = off; off += sz_ctab;
   g.off_bar = off;  off += 512;
@@ -1030,7 +1032,7 @@ struct TcsParams {
   int BN, nb, nD, nst;
   int bn_shift, w_shift;
   int tiles_per_img; int ntiles;
-  uint32_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_pz, off_zn, off_ctab, off_bar;
+  uint32_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_bar;
   int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
   float* sums; float* sums_rep; int nrep;
   int* fb_count; int* fb_rows;
@@ -1058,7 +1060,6 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       mbar_init(BAR(TCS_B_AFULL + i), 1); mbar_init(BAR(TCS_B_AEMPTY + i), 1);
       mbar_init(BAR(TCS_B_TFULL + i), 1); mbar_init(BAR(TCS_B_TEMPTY + i), TC_SCAN_WARPS);
       mbar_init(BAR(TCS_B_ZN + i), 2);
-      mbar_init(BAR(TCS_B_PFULL + i), TC_SCAN_WARPS); mbar_init(BAR(TCS_B_PEMPTY + i), TC_OUT_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1199,29 +1200,47 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
       }
     }
-  } else if (warp < TC_AUX_WARPS + TC_SCAN_WARPS) {
-    // ===================================== scan warps (as in the resident kernel) ==========================
-    const int quad = warp & 3, cg = (warp - TC_AUX_WARPS) >> 2;
-    const int p = quad * 32 + lane;
+  } else {
+    // ===================================== epilogue warps: two teams of eight ================================
+    // Team t takes the tiles it = t, t+2, ... of this CTA and does everything for them: scan (warp = TMEM lane quadrant
+    // x column group, as in the resident kernel), merge, exact re-rank, outputs.  The scan of a tile is short next to
+    // its output phase here (z and the code rows come from L2, D/8 dependent round trips per lane), so while one team
+    // is writing a tile out the other one already scans and writes the next: twice the loads in flight.
+    const int ew = warp - TC_AUX_WARPS, team = ew >> 3, tw = ew & 7;
+    const int quad = warp & 3, cg = tw >> 2;              // warp % 4 == TMEM lane quadrant this warp may read
+    const int p = quad * 32 + lane;                       // scan: pixel within the tile == TMEM lane
     const uint32_t ctab_s = sbase + P.off_ctab;
-    const uint32_t zn_s = sbase + P.off_zn + (uint32_t)p * 4;
-    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)(cg * TC_TILE + p) * 16;
+    const uint32_t zn_s = sbase + P.off_zn + (uint32_t)(team * TC_TILE + p) * 4;
     const int nchunks = P.BN >> 5;
-    int g = 0;
-    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // only for the debug dump
+    // output phase: lane = (pixel px, quad parity hf) of the 16 pixels quad*32 + cg*16 .. +15
+    const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
+    const int po = quad * 32 + cg * TC_OPX + px;
+    const float rminbig = __uint_as_float(P.meta[1]);
+    const int D = P.D, nq = D >> 2;
+    float* sums_mine = nullptr;
+    if (STATS) {
+      const int rep = (int)((blockIdx.x * 2 + team) % (unsigned)P.nrep);
+      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * D;
+    }
+    const size_t hw = (size_t)P.HW;
+    const size_t img_stride = (size_t)D * hw;
+    float2 ls2 = make_float2(0.f, 0.f);
     TC_TIMING_DECL
-    for (int it = 0; it < my_tiles; ++it) {
-      const int sl = it & 1, sph = (it >> 1) & 1;
-      TC_TICK(4);
-      mbar_wait(BAR(TCS_B_ZN + sl), sph);
+    for (int it = team; it < my_tiles; it += 2) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
+      const int n2 = it >> 1;                             // this team's tile counter
+      TC_TICK(5);
+      mbar_wait(BAR(TCS_B_ZN + team), n2 & 1);
       TC_TICK(0);
-      float z2;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(zn_s + (uint32_t)sl * (TC_TILE * 4)));
-      const float zn = sqrtf(z2) * 1.00001f;
+      float z2s;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2s) : "r"(zn_s));
+      const float zn_scan = sqrtf(z2s) * 1.00001f;
       float L = -INFINITY, Urec = -INFINITY;
       int cnt = 0;
       uint32_t rcA = 0, rcB = 0, rm0 = 0, rm1 = 0;
-      for (int blk = 0; blk < P.nb; ++blk, ++g) {
+      for (int blk = 0; blk < P.nb; ++blk) {
+        const int g = it * P.nb + blk;
         const int a = g & 1, aph = (g >> 1) & 1;
         TC_TICK(2);
         mbar_wait(BAR(TCS_B_TFULL + a), aph);
@@ -1234,10 +1253,10 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           const int gc = blk * nchunks + c;
           float cA, cB;
           asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)gc * 8));
-          const float delta = __fmaf_rn(zn, cA, cB);
+          const float delta = __fmaf_rn(zn_scan, cA, cB);
           tmem_ld_wait();
           if (DBG) {
-            float* o = P.dbg + ((size_t)tb * P.HW + tpt * TC_TILE + p) * ktot + gc * 32;
+            float* o = P.dbg + ((size_t)b * P.HW + p0 + p) * ktot + gc * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = v[j];
           }
@@ -1278,67 +1297,33 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(TCS_B_TEMPTY + a));
       }
-      if (DBG) { tpt += (int)gridDim.x; while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; } }
+      // ---- publish to the team: {L, U16 | chunkA<<8 | chunkB<<1 | overflow, maskA, maskB}, double-buffered by tile parity
       if (cnt < 2) rm1 = 0;
       if (cnt < 1) rm0 = 0;
       const uint32_t w1 = f32_up16(Urec) | (rcA << 8) | (rcB << 1) | (cnt > 2 ? 1u : 0u);
-      const int par = it & 1, pph = (it >> 1) & 1;
+      const uint32_t pub_t = sbase + P.off_pub + (uint32_t)((team * 2 + (n2 & 1)) * TC_NCG) * (TC_TILE * 16);
       TC_TICK(2);
-      mbar_wait(BAR(TCS_B_PEMPTY + par), pph ^ 1);
-      TC_TICK(3);
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_s + (uint32_t)par * (TC_NCG * TC_TILE * 16)),
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_t + (uint32_t)(cg * TC_TILE + p) * 16),
                    "r"(__float_as_uint(L)), "r"(w1), "r"(rm0), "r"(rm1) : "memory");
-      // the |z|^2 slot may be rewritten (tile it+2) before the output warps get to this tile: forward it with the results
-      if (cg == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbase + P.off_pz + (uint32_t)(par * TC_TILE + p) * 4), "f"(z2) : "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(TCS_B_PFULL + par));
-    }
-    TC_TIMING_STORE(warp - TC_AUX_WARPS, my_tiles);
-  } else {
-    // ===================================== output warps =====================================
-    // Same decisions as in the resident kernel (lane = pixel x quad parity); z and the exact fp32 code rows come from
-    // global memory (L2 hits: the tile and the codebook were just streamed), so these warps never touch the ring.
-    const int ow = warp - TC_AUX_WARPS - TC_SCAN_WARPS;
-    const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
-    const int p = ow * TC_OPX + px;
-    const float rminbig = __uint_as_float(P.meta[1]);
-    const int D = P.D, nq = D >> 2;
-    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)p * 16;
-    const uint32_t pz_s = sbase + P.off_pz + (uint32_t)p * 4;
-    float* sums_mine = nullptr;
-    if (STATS) {
-      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
-      sums_mine = rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * D;
-    }
-    const size_t hw = (size_t)P.HW;
-    const size_t img_stride = (size_t)D * hw;
-    float2 ls2 = make_float2(0.f, 0.f);
-    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;
-    TC_TIMING_DECL
-    for (int it = 0; it < my_tiles; ++it) {
-      const int sl = it & 1, sph = (it >> 1) & 1;
-      const int b = tb, p0 = tpt * TC_TILE;
-      tpt += (int)gridDim.x;
-      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
-      const int pp = p0 + p;
-      const float* zp = P.z + (size_t)b * img_stride + pp;           // z(pixel, channel d) = zp[d * hw]
-      TC_TICK(4);
-      mbar_wait(BAR(TCS_B_PFULL + sl), sph);
-      TC_TICK(1);
-      float z2;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z2) : "r"(pz_s + (uint32_t)sl * (TC_TILE * 4)));
+      // team barrier (hardware named barrier: a waiting warp issues nothing).  A warp cannot be two tiles ahead of a
+      // team mate (it needs the mate's arrival at the next barrier), so two publication buffers per team are enough.
+      if (team == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+
+      // ---- merge the column groups of my output pixel ---------------------------------------------------------
+      const float z2 = __shfl_sync(0xffffffffu, z2s, cg * TC_OPX + px);     // scan lane (pixel po) of this very warp
       const float zn = sqrtf(z2) * 1.00001f;
       const bool bad = !(z2 <= 3.0e38f);
+      const int pp = p0 + po;
+      const float* zp = P.z + (size_t)b * img_stride + pp;           // z(pixel, channel d) = zp[d * hw]
       uint32_t pw[TC_NCG][4];
       float Lg = -INFINITY;
 #pragma unroll
       for (int i = 0; i < TC_NCG; ++i) {
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pw[i][0]), "=r"(pw[i][1]), "=r"(pw[i][2]), "=r"(pw[i][3])
-                     : "r"(pub_s + (uint32_t)(sl * TC_NCG + i) * (TC_TILE * 16)));
+                     : "r"(pub_t + (uint32_t)(i * TC_TILE + po) * 16));
         Lg = fmaxf(Lg, __uint_as_float(pw[i][0]));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(TCS_B_PEMPTY + sl));
       int total = 0;
       bool ovf = false;
 #pragma unroll
@@ -1364,7 +1349,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
       }
       int worig = __ldg(P.perm + w);
-      TC_TICK(2);
+      TC_TICK(3);
       // ---- pixels with several candidates: exact fp32 re-rank by the pixel's own two lanes (see the resident kernel) ----
       // (a variant with the whole warp on one (pixel, code) pair and the fma chains travelling from lane to lane was
       //  slower: at D = 256 a warp has 3-4 such pixels per tile and they are better served in parallel)
@@ -1420,7 +1405,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         if (!fb && total > 1) worig = 0xFFFF - (int)((key >> 16) & 0xFFFFull);
       }
 
-      TC_TICK(3);
+      TC_TICK(4);
       // ---- outputs ------------------------------------------------------------------------------------
       if (fb) {
         if (hf == 0) {
@@ -1474,8 +1459,8 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
       }
     }
-    TC_TICK(4);
-    TC_TIMING_STORE(8 + ow, my_tiles);
+    TC_TICK(5);
+    TC_TIMING_STORE(ew, my_tiles);
     float lsum = ls2.x + ls2.y;
     lsum = warp_sum(lsum);
     if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
@@ -1662,7 +1647,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
   P.ntiles = a.B * P.tiles_per_img;
   P.stage_bytes = (uint32_t)g.stage_bytes; P.off_stage = (uint32_t)g.off_stage;
   P.off_aug = (uint32_t)g.off_aug; P.off_aaug = (uint32_t)g.off_aaug;
-  P.off_pub = (uint32_t)g.off_pub; P.off_pz = (uint32_t)g.off_pz; P.off_zn = (uint32_t)g.off_zn;
+  P.off_pub = (uint32_t)g.off_pub; P.off_zn = (uint32_t)g.off_zn;
   P.off_ctab = (uint32_t)g.off_ctab; P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
   P.counts = a.stats ? a.ws.counts : nullptr;

@@ -10,6 +10,7 @@ import medical_image_editing_b200 as pkg
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+data = sys.argv[4] if len(sys.argv) > 4 else "noise"      # noise | clustered (z = code + 0.1 noise) | relu
 H = 256
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(1)
@@ -20,7 +21,15 @@ with torch.no_grad():
     cs = torch.rand(K, generator=torch.Generator().manual_seed(1234)) * (N / K) + 1.0
     m.cluster_size.copy_(cs.to(dev))
     m.embed_avg.copy_((m.embed * m.cluster_size[:, None]).T)
-z = [torch.randn(B, D, H, H, device=dev, generator=g) for _ in range(4)]
+if data == "clustered":
+    def mk():
+        idx = torch.randint(0, K, (B, H, H), device=dev, generator=g)
+        return (m.embed.detach()[idx].permute(0, 3, 1, 2) + 0.1 * torch.randn(B, D, H, H, device=dev, generator=g)).contiguous()
+    z = [mk() for _ in range(4)]
+elif data == "relu":
+    z = [torch.relu(torch.randn(B, D, H, H, device=dev, generator=g)) for _ in range(4)]
+else:
+    z = [torch.randn(B, D, H, H, device=dev, generator=g) for _ in range(4)]
 out = []
 for train in (True, False):
     m.train(train)
@@ -41,4 +50,4 @@ for train in (True, False):
         L.vq_profile_read(ctypes.byref(tot), ctypes.byref(nl))
         L.vq_profile_enable(0)
         out.append(f"{'train' if train else 'eval '} kernel {tot.value / max(nl.value, 1):.4f} ms fwd {e0.elapsed_time(e1) / n:.4f} ms")
-print(os.environ.get("VQ_B200_LIB", "default"), f"D={D} K={K}:", " | ".join(out))
+print(os.environ.get("VQ_B200_LIB", "default"), f"D={D} K={K} {data}:", " | ".join(out))

@@ -40,6 +40,16 @@ if n > 0:
     t = buf.reshape(148, 16, 8).astype(np.float64)
     tiles = t[:, :, 6].mean()
     print(f"tiles per CTA {tiles:.1f}")
+    streamed = K * D * 4 > 140 * 1024
+    if streamed:      # streamed-codebook kernel: 16 epilogue warps in two teams, every warp does scan + outputs for its tiles
+        names = ["wait |z|^2", "wait tmem", "scan work", "team barrier+merge", "re-rank", "outputs+loop"]
+        r = t[:, :, :]
+        tiles_w = r[:, :, 6] / 2.0          # each team takes every other tile
+        print(f"epilogue warps: cycles per (own) tile {(r[:, :, :6].sum(axis=2) / tiles_w).mean():.0f}")
+        for i, nm in enumerate(names):
+            per = r[:, :, i] / tiles_w
+            print(f"  {nm:20s} mean {per.mean():8.0f}  min {per.min():8.0f}  max {per.max():8.0f}")
+        sys.exit(0)
     for role, sl, names in (("scan warps", slice(0, 8), ["wait |z|^2", "wait tmem", "scan work", "wait pub slot", "publish+loop"]),
                             ("output warps", slice(8, 16), ["wait z/|z|^2", "wait scan", "merge", "pairs+rerank", "outputs"])):
         r = t[:, sl, :]
