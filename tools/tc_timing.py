@@ -1,6 +1,6 @@
 """Phase timing of the tensor-core epilogue.  Build first with
    VQ_EXTRA_FLAGS=-DVQ_TC_TIMING FORCE=1 bash medical_image_editing_b200/csrc/build.sh
-then run on the GPU box:  python tools/tc_timing.py [D K B train]"""
+then run on the GPU box:  python tools/tc_timing.py [D K B train noise|clustered]"""
 import ctypes
 import sys
 import os
@@ -13,6 +13,7 @@ D = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 train = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
+data = sys.argv[5] if len(sys.argv) > 5 else "noise"        # noise | clustered (z = code + 0.1 noise)
 H = 256
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(1)
@@ -22,7 +23,11 @@ with torch.no_grad():
     m.cluster_size.fill_(2048.0)
     m.embed_avg.copy_(m.embed.T * 2048.0)       # consistent EMA state: embed == embed_avg / cluster_size
 m.train(train)
-z = [torch.randn(B, D, H, H, device=dev, generator=g) for _ in range(3)]
+if data == "clustered":
+    z = [(m.embed.detach()[torch.randint(0, K, (B, H, H), device=dev, generator=g)].permute(0, 3, 1, 2)
+          + 0.1 * torch.randn(B, D, H, H, device=dev, generator=g)).contiguous() for _ in range(3)]
+else:
+    z = [torch.randn(B, D, H, H, device=dev, generator=g) for _ in range(3)]
 with torch.no_grad():
     for i in range(3):
         m(z[i])
