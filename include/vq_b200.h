@@ -128,6 +128,24 @@ int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D,
               float* out, int layout, int B, int A, int C, int* status, vq_stream_t stream);
 
 /*
+ * Cross-view cluster loss of EmbeddingLoss._calc_cross_loss (src/functions/embed_loss.py:46-66), the consumer of the
+ * quantiser's outputs in the stage-1 trainers (single_window_trainer.py:91-105); SURVEY section 8(f), rank 1.
+ *   loss = mean over the (b, k) that occur of  sum_{loc: labels[b, loc] == k + 1} |z[b, :, loc] - embed[k]|^2
+ *                                              / (count[b, k] + 1e-6)
+ *   labels  int32 [B][H*W]: 0 = no class at this location, k + 1 = class k -- the integer map the reference one-hot
+ *           encodes and strips of class 0 (single_window_trainer.py:91-99) before it multiplies by it;
+ *   embed   [K][D] row-major (= codebook^T, VQModule.embed; the loss detaches it, embed_loss.py:51);
+ *   weights out, float [B*K]: 1 / ((count + 1e-6) * #present) for vq_embed_loss_bwd (0 where (b, k) does not occur);
+ *   work    device scratch of vq_embed_loss_work_bytes(B, K) bytes, 256-byte aligned;
+ *   vq_embed_loss_bwd: g_z = g_loss * 2 * weights[b, k] * (z - embed[k]) at labelled locations, 0 elsewhere.
+ */
+size_t vq_embed_loss_work_bytes(int B, int K);
+int vq_embed_loss_fwd(const float* z, const int32_t* labels, const float* embed, int B, int D, int H, int W, int K,
+                      float* loss, float* weights, void* work, size_t work_bytes, vq_stream_t stream);
+int vq_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels, const float* embed,
+                      const float* weights, float* g_z, int B, int D, int H, int W, int K, vq_stream_t stream);
+
+/*
  * Measurement hooks (used by bench.py only; they do not change results).
  *   vq_launch_count     number of kernels this library has launched in this process so far.
  *   vq_profile_enable   when on, vq_assign_fwd brackets its dominant kernel (the nearest-code

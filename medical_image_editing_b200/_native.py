@@ -41,6 +41,11 @@ SIGNATURES = {
     "vq_lookup": (ctypes.c_int, [c_i64p, ctypes.c_int64, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i32p,
                                  ctypes.c_void_p]),
+    "vq_embed_loss_work_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "vq_embed_loss_fwd": (ctypes.c_int, [c_f32p, c_i32p, c_f32p] + [ctypes.c_int] * 5 +
+                          [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "vq_embed_loss_bwd": (ctypes.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 5 +
+                          [ctypes.c_void_p]),
     "vq_launch_count": (ctypes.c_int64, []),
     "vq_debug_tc_ncols": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "vq_debug_tc_scores": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32p,

@@ -89,6 +89,35 @@ int vq_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t*
   return launch_bwd(g_q, g_loss, z, ids_nat, embed_snapshot, g_z, B, D, H, W, K, (cudaStream_t)stream);
 }
 
+size_t vq_embed_loss_work_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return embed_loss_work_bytes(B, K);
+}
+
+int vq_embed_loss_fwd(const float* z, const int32_t* labels, const float* embed, int B, int D, int H, int W, int K,
+                      float* loss, float* weights, void* work, size_t work_bytes, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B > 0 && D > 0 && H >= 0 && W >= 0 && K > 0, VQ_ERR_INVALID_ARG,
+             "vq_embed_loss_fwd: bad shape B=%d D=%d H=%d W=%d K=%d", B, D, H, W, K);
+  VQ_REQUIRE((int64_t)B * K < (int64_t)1 << 31 && (int64_t)B * H * W < (int64_t)1 << 31, VQ_ERR_UNSUPPORTED,
+             "vq_embed_loss_fwd: B*K and B*H*W must be < 2^31");
+  VQ_REQUIRE(embed && loss && weights && work, VQ_ERR_INVALID_ARG, "vq_embed_loss_fwd: null pointer");
+  VQ_REQUIRE((int64_t)B * H * W == 0 || (z && labels), VQ_ERR_INVALID_ARG, "vq_embed_loss_fwd: null z/labels");
+  VQ_REQUIRE(((uintptr_t)work & 255) == 0, VQ_ERR_INVALID_ARG, "vq_embed_loss_fwd: work must be 256-byte aligned");
+  VQ_REQUIRE(work_bytes >= embed_loss_work_bytes(B, K), VQ_ERR_WORKSPACE, "vq_embed_loss_fwd: work too small (%zu < %zu)",
+             work_bytes, embed_loss_work_bytes(B, K));
+  return launch_embed_loss_fwd(z, labels, embed, B, D, H, W, K, loss, weights, work, (cudaStream_t)stream);
+}
+
+int vq_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels, const float* embed,
+                      const float* weights, float* g_z, int B, int D, int H, int W, int K, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B > 0 && D > 0 && H >= 0 && W >= 0 && K > 0, VQ_ERR_INVALID_ARG, "vq_embed_loss_bwd: bad shape");
+  if ((int64_t)B * H * W == 0) return VQ_OK;
+  VQ_REQUIRE(g_loss && z && labels && embed && weights && g_z, VQ_ERR_INVALID_ARG, "vq_embed_loss_bwd: null pointer");
+  return launch_embed_loss_bwd(g_loss, z, labels, embed, weights, g_z, B, D, H, W, K, (cudaStream_t)stream);
+}
+
 int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout, int B, int A,
               int C, int* status, vq_stream_t stream) {
   set_error("");

@@ -117,6 +117,12 @@ int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int3
                const float* snap, float* g_z, int B, int D, int H, int W, int K, cudaStream_t s);
 int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout,
                   int B, int A, int C, int* status, cudaStream_t s);
+// vq_embed_loss.cu: cross-view cluster loss of EmbeddingLoss (functions/embed_loss.py)
+size_t embed_loss_work_bytes(int B, int K);
+int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* embed, int B, int D, int H, int W, int K,
+                          float* loss, float* weights, void* work, cudaStream_t s);
+int launch_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels, const float* embed,
+                          const float* weights, float* g_z, int B, int D, int H, int W, int K, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
