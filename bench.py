@@ -165,6 +165,9 @@ def run_reference_arm(args, wl, wl_name):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
+    # rank 0 alone times the CPU path: the reference gates its all_reduce on $WORLD_SIZE (utils/__init__.py:109-114),
+    # which torchrun sets for the N > 1 launches -- this leg is a single process without a process group
+    os.environ["WORLD_SIZE"] = "1"
     slices = 2
     step, n = cpu_step_factory(wl, slices)
     for _ in range(max(1, min(args.warmup, 2))):
