@@ -135,6 +135,37 @@ def test_seeded_vs_oracle(K, D, kind, flags):
     assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
 
 
+# tile counts that are not a multiple of the grid, single-tile and two-tile launches, odd quad counts: the streamed-codebook
+# kernel splits the tiles of a CTA between two teams of epilogue warps (a team may get no tile at all)
+MULTI_TILE = [(5, 96, 512, 256, "gauss"), (3, 128, 600, 132, "clustered"), (1, 16, 512, 256, "gauss"),
+              (7, 64, 4096, 68, "gauss"), (9, 48, 512, 128, "relu"), (4, 80, 512, 64, "gauss"), (11, 32, 64, 64, "clustered")]
+
+
+@pytest.mark.parametrize("B,H,K,D,kind", MULTI_TILE)
+def test_multi_tile_vs_oracle(B, H, K, D, kind):
+    z, embed = seeded_case(B, D, H, H, K, seed=4242 + K + D + B, kind=kind)
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H, chunk=8192)
+    m = new_vq(K, D, 0.99, 0)
+    assert pkg.lib().vq_assign_path(B, D, H, H, K, 0) == 1, "this shape should take the tensor-core path"
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    ora.train(True)
+    m.train(True)
+    z_ref = z.clone().requires_grad_(True)
+    q_ref, loss_ref, ids_ref = ora(z_ref)
+    (gz_ref,) = torch.autograd.grad(q_ref.sum() + 0.3 * loss_ref, z_ref)
+    z_gpu = z.to(DEV).requires_grad_(True)
+    q, loss, ids = m(z_gpu)
+    (gz,) = torch.autograd.grad(q.sum() + 0.3 * loss, z_gpu)
+    nties = assert_ids_match(ids, ids_ref, embed, z)
+    if nties == 0:
+        assert torch.equal(q.detach().cpu(), q_ref.detach().contiguous())
+        assert rel_err(m.cluster_size, ora.cluster_size) <= TOL
+        assert rel_err(m.embed_avg, ora.embed_avg) <= TOL
+        assert rel_err(m.embed, ora.embed) <= TOL
+        assert rel_err(gz, gz_ref) <= TOL
+    assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
+
+
 @pytest.mark.parametrize("flags", PATHS)
 def test_cold_start_exploded_codes(flags):
     """First EMA step with cluster_size == 0 blows unused codes up to ~1e5 x (SURVEY section 7);
