@@ -1010,9 +1010,11 @@ static TcsGeom tcs_geometry(int D, int K) {
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
   int nst = (int)(room / (long long)g.stage_bytes);
   if (nst > TCS_MAX_ST) nst = TCS_MAX_ST;
-  // the |z|^2 slot of tile it is rewritten for tile it+2: the producer must not run that far ahead of the tensor core
-  // (its first block of tile it+1 starts only after the team has read the slot) -- see the epilogue warps
-  if (nst > (g.nb + 1) * g.nD - 1) nst = (g.nb + 1) * g.nD - 1;
+  // The |z|^2 slot (and barrier) of tile it is reused for tile it+2, so |z|^2(it+2) must not complete before the team of
+  // tile it has read |z|^2(it).  The team reads it before it scans block (it, 0); the MMA of block it*nb + 2 starts only
+  // after that scan (TMEM has two stages); |z|^2(it+2) needs the last chunk of block (it+2, 0) loaded, and the producer
+  // is at most nst stages ahead of the tensor core: nst <= ((it+2) nb nD + nD - 1) - (it nb + 2) nD = (2 nb - 1) nD - 1.
+  if (nst > (2 * g.nb - 1) * g.nD - 1) nst = (2 * g.nb - 1) * g.nD - 1;
   if (nst < 2) return g;
   g.nst = nst;
   off += (size_t)nst * g.stage_bytes;
@@ -1510,7 +1512,9 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
   const TcGeom g = tc_geometry(a.D, a.K);
-  if (!(g.ok && g.nb * g.BN <= TC_SORT_MAX) && tcs_supported(a.D, a.K)) return launch_assign_tcs_impl(a, dbg, s);
+  // resident codebook only when two z stages fit beside it (one stage = no prefetch: D = 256 at K = 64 ran 1.5x slower
+  // than the streamed kernel)
+  if (!(g.ok && g.nst == 2 && g.nb * g.BN <= TC_SORT_MAX) && tcs_supported(a.D, a.K)) return launch_assign_tcs_impl(a, dbg, s);
   VQ_REQUIRE(g.ok && g.nb * g.BN <= TC_SORT_MAX && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path: unsupported shape");
   VQ_REQUIRE(a.q != nullptr || dbg != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
   EncodeTiledFn enc = get_encode_fn();
@@ -1693,7 +1697,7 @@ int tc_debug_timing(long long* host_out, int n) {
 
 int tc_debug_ncols(int D, int K) {
   const TcGeom g = tc_geometry(D, K);
-  if (g.ok && g.nb * g.BN <= TC_SORT_MAX) return g.nb * g.BN;
+  if (g.ok && g.nb * g.BN <= TC_SORT_MAX && (g.nst == 2 || !tcs_geometry(D, K).ok)) return g.nb * g.BN;
   const TcsGeom gs = tcs_geometry(D, K);
   return gs.ok ? gs.nb * gs.BN : 0;
 }

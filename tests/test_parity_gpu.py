@@ -138,7 +138,9 @@ def test_seeded_vs_oracle(K, D, kind, flags):
 # tile counts that are not a multiple of the grid, single-tile and two-tile launches, odd quad counts: the streamed-codebook
 # kernel splits the tiles of a CTA between two teams of epilogue warps (a team may get no tile at all)
 MULTI_TILE = [(5, 96, 512, 256, "gauss"), (3, 128, 600, 132, "clustered"), (1, 16, 512, 256, "gauss"),
-              (7, 64, 4096, 68, "gauss"), (9, 48, 512, 128, "relu"), (4, 80, 512, 64, "gauss"), (11, 32, 64, 64, "clustered")]
+              (7, 64, 4096, 68, "gauss"), (9, 48, 512, 128, "relu"), (4, 80, 512, 64, "gauss"), (11, 32, 64, 64, "clustered"),
+              # single-block codebooks in the streamed kernel (the ring may not run a whole tile ahead of the tensor core)
+              (6, 64, 64, 256, "gauss"), (5, 64, 256, 256, "clustered"), (13, 32, 64, 192, "gauss"), (3, 96, 40, 224, "relu")]
 
 
 @pytest.mark.parametrize("B,H,K,D,kind", MULTI_TILE)
