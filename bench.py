@@ -225,7 +225,9 @@ def run_b200_arm(args, wl, wl_name):
     zbufs = [torch.randn(B, D, H, H, device=dev, generator=gen).requires_grad_(True) for _ in range(NBUF)]
     g_q = torch.randn(B, D, H, H, device=dev, generator=gen)
     one = torch.ones((), device=dev)
-    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch").to(dev)
+    # N > 1: the all-reduce of the EMA statistics and the EMA update run on a side stream, behind the backward
+    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch",
+                overlap_exchange=(world > 1 and not args.inline_exchange)).to(dev)
     if args.simt:
         vq.kernel_flags = 1
     vq.train(True)
@@ -393,7 +395,9 @@ def run_b200_arm(args, wl, wl_name):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(wl, wl_name, world, extra={"search_path": "tcgen05+fp32-rerank" if path == 1 else "fp32-cuda-core",
-                                                          "ema_state": "cold" if args.cold else "warmed"}),
+                                                          "ema_state": "cold" if args.cold else "warmed",
+                                                          "stats_exchange": ("none" if world == 1 else "inline" if args.inline_exchange
+                                                                             else "packed all-reduce + EMA on a side stream")}),
             "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": z_host[0].numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
                     "overlap": "step i+1 H2D (copy stream, double buffer) overlaps step i kernels; result read every step",
@@ -420,6 +424,7 @@ def main():
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
+    ap.add_argument("--inline-exchange", action="store_true", help="N > 1: all-reduce + EMA update on the compute stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]

@@ -25,6 +25,25 @@ except ImportError:  # dropped into the reference tree (src/functions/vq_functio
 REDUCE_MODES = ("sum", "mean", "reference")
 
 _WORKSPACES = {}
+_SIDE_STREAMS = {}        # device index -> stream of the overlapped statistics exchange
+_PENDING = {}             # embed.data_ptr() -> event recorded after an overlapped all-reduce + EMA update
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[device.index] = st
+    return st
+
+
+def wait_pending_update(embed: torch.Tensor) -> None:
+    """Make the current stream wait for an overlapped EMA update of this codebook (no-op when none is in flight).
+    Called before anything reads or writes the buffers: the next forward, `lookup`, `get_codebook`, `state_dict`."""
+    ev = _PENDING.pop(embed.data_ptr(), None) if embed.is_cuda else None
+    if ev is not None:
+        torch.cuda.current_stream(embed.device).wait_event(ev)
+
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -85,7 +104,7 @@ class VQFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, embed, cluster_size, embed_avg, momentum, eps, training,
-                reduce_mode="sum", flags=0):
+                reduce_mode="sum", flags=0, overlap_exchange=False):
         _require_cuda(z, "input")
         _require_cuda(embed, "embed")
         if z.dim() != 4:
@@ -113,22 +132,46 @@ class VQFunction(torch.autograd.Function):
             stats = torch.empty(L.vq_stats_floats(K, D), dtype=torch.float32, device=dev) if training else None
             nbytes = L.vq_workspace_bytes(B * H * W, K, D)
             ws = _workspace(dev, nbytes)
+            wait_pending_update(embed)          # an overlapped update of the previous step must land first
             check(L.vq_assign_fwd(zc.data_ptr(), B, D, H, W, ec.data_ptr(), K, ids.data_ptr(), _ptr(ids_nat),
                                   q.data_ptr(), loss.data_ptr(), _ptr(stats), _ptr(snap),
                                   ws.data_ptr(), ws.numel(), int(flags), _stream()), "vq_assign_fwd")
             if training:
-                cscale, sscale = 1.0, 1.0
-                if is_distributed():
-                    cscale, sscale = _all_reduce_stats(stats, K, reduce_mode)
                 if not (cluster_size.is_contiguous() and embed.is_contiguous()):
                     raise RuntimeError("B200 VQ: the embed / cluster_size buffers must be contiguous")
                 if tuple(embed_avg.shape) != (D, K) or tuple(cluster_size.shape) != (K,):
                     raise RuntimeError("B200 VQ: embed_avg must be [emb_dim, dict_size] and cluster_size [dict_size]")
                 # embed_avg = embed.T.clone() keeps strides (1, D) (vq_module.py:156): pass them through
                 sd, sk = embed_avg.stride()
-                check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), sd, sk, embed.data_ptr(),
-                                      stats.data_ptr(), K, D, float(momentum), float(eps), cscale, sscale,
-                                      ws.data_ptr(), _stream()), "vq_ema_update")
+
+                def exchange_and_update(stream_handle):
+                    cscale, sscale = 1.0, 1.0
+                    if is_distributed():
+                        cscale, sscale = _all_reduce_stats(stats, K, reduce_mode)
+                    check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), sd, sk, embed.data_ptr(),
+                                          stats.data_ptr(), K, D, float(momentum), float(eps), cscale, sscale,
+                                          scratch.data_ptr(), stream_handle), "vq_ema_update")
+
+                if overlap_exchange and is_distributed():
+                    # The updated codebook is not needed before the next forward (q was gathered from the old one,
+                    # the backward uses the snapshot): run the all-reduce and the EMA update on a side stream so they
+                    # overlap whatever the caller enqueues next (the backward, the decoder); `wait_pending_update`
+                    # joins the streams before the buffers are touched again.
+                    cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                    scratch = torch.empty(64, dtype=torch.uint8, device=dev)
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    side.wait_event(ready)
+                    with torch.cuda.stream(side):
+                        exchange_and_update(side.cuda_stream)
+                        done = torch.cuda.Event()
+                        done.record(side)
+                    for t_ in (stats, scratch):
+                        t_.record_stream(side)
+                    _PENDING[embed.data_ptr()] = done
+                else:
+                    scratch = ws
+                    exchange_and_update(_stream())
         if need_bwd:
             ctx.save_for_backward(zc, ids_nat, snap)
         ctx.shape = (B, D, H, W, K)
@@ -148,7 +191,7 @@ class VQFunction(torch.autograd.Function):
             g_z = torch.empty_like(zc)
             check(lib().vq_bwd(_ptr(g_q), _ptr(g_loss), zc.data_ptr(), ids_nat.data_ptr(), snap.data_ptr(),
                                g_z.data_ptr(), B, D, H, W, K, _stream()), "vq_bwd")
-        return g_z, None, None, None, None, None, None, None, None
+        return g_z, None, None, None, None, None, None, None, None, None
 
 
 def vq_lookup(ids: torch.Tensor, embed: torch.Tensor, nchw_friendly: bool = True) -> torch.Tensor:
@@ -168,6 +211,7 @@ def vq_lookup(ids: torch.Tensor, embed: torch.Tensor, nchw_friendly: bool = True
     K, D = embed.shape
     L = lib()
     dev = embed.device
+    wait_pending_update(embed)
     debug = os.environ.get("VQ_B200_CHECK_IDS", "0") == "1"
     with torch.cuda.device(dev):
         idc = ids.contiguous()

@@ -477,7 +477,7 @@ def test_embed_avg_layouts():
 # ---------------------------------------------------------------------------------------------
 # multi-GPU: 2 NCCL ranks == one process on the concatenated batch (skipped on single-GPU boxes)
 # ---------------------------------------------------------------------------------------------
-def _nccl_worker(rank, ws, port, ret):
+def _nccl_worker(rank, ws, port, ret, overlap):
     import os
     import torch.distributed as dist
     os.environ.update(WORLD_SIZE=str(ws), RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -486,33 +486,42 @@ def _nccl_worker(rank, ws, port, ret):
     dev = f"cuda:{rank}"
     B, D, H, K = 4, 64, 128, 512
     gen = torch.Generator().manual_seed(77)
-    z = torch.randn(B, D, H, H, generator=gen)
+    zs = [torch.randn(B, D, H, H, generator=gen) for _ in range(2)]
     embed = torch.randn(K, D, generator=gen)
-    m = pkg.VQ(emb_dim=D, dict_size=K, momentum=0.99, eps=1e-5, knn_backend="torch", reduce_mode="sum").to(dev)
+    m = pkg.VQ(emb_dim=D, dict_size=K, momentum=0.99, eps=1e-5, knn_backend="torch", reduce_mode="sum",
+               overlap_exchange=overlap).to(dev)
     with torch.no_grad():
         m.embed.copy_(embed)
         m.embed_avg.copy_(embed.T)
         m.cluster_size.fill_(1.0)
     m.train(True)
     half = B // ws
-    q, loss, ids = m(z[rank * half:(rank + 1) * half].to(dev))
+    out = {}
+    for s_, z in enumerate(zs):                    # two steps: the second forward must see the first step's update
+        zr = z[rank * half:(rank + 1) * half].to(dev).requires_grad_(True)
+        q, loss, ids = m(zr)
+        (gz,) = torch.autograd.grad(q.sum() + loss, zr)      # backward overlaps the exchange when `overlap`
+        out[f"ids{s_}"] = ids.cpu().numpy()
+    out["embed"] = m.get_codebook().t().contiguous().cpu().numpy()      # joins the side stream
+    out["cs"] = m.state_dict()["cluster_size"].cpu().numpy()
     torch.cuda.synchronize()
-    ret[rank] = dict(ids=ids.cpu().numpy(), embed=m.embed.cpu().numpy(), cs=m.cluster_size.cpu().numpy())
+    ret[rank] = out
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_nccl_matches_single_process():
+@pytest.mark.parametrize("overlap", [False, True], ids=["inline", "overlapped"])
+def test_two_rank_nccl_matches_single_process(overlap):
     import os
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_nccl_worker, args=(2, 29761, ret), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, 29761 + int(overlap), ret, overlap), nprocs=2, join=True)
     os.environ.pop("WORLD_SIZE", None)
     os.environ.pop("RANK", None)
     B, D, H, K = 4, 64, 128, 512
     gen = torch.Generator().manual_seed(77)
-    z = torch.randn(B, D, H, H, generator=gen)
+    zs = [torch.randn(B, D, H, H, generator=gen) for _ in range(2)]
     embed = torch.randn(K, D, generator=gen)
     m = new_vq(K, D, 0.99, 0)
     with torch.no_grad():
@@ -520,8 +529,9 @@ def test_two_rank_nccl_matches_single_process():
         m.embed_avg.copy_(embed.T.to(DEV))
         m.cluster_size.fill_(1.0)
     m.train(True)
-    _, _, ids = m(z.to(DEV))
-    assert np.array_equal(np.concatenate([ret[0]["ids"], ret[1]["ids"]]), ids.cpu().numpy())
+    for s_, z in enumerate(zs):
+        _, _, ids = m(z.to(DEV))
+        assert np.array_equal(np.concatenate([ret[0][f"ids{s_}"], ret[1][f"ids{s_}"]]), ids.cpu().numpy())
     for r in range(2):
         assert np.array_equal(ret[r]["cs"], m.cluster_size.cpu().numpy())
         assert rel_err(t(ret[r]["embed"]), m.embed) <= TOL
