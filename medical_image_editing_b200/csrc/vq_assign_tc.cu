@@ -1,26 +1,30 @@
 // vq_assign_tc.cu -- tcgen05 / TMEM / TMA nearest-code search with exact fp32 re-rank (sm_100a).
 //
-// One persistent CTA per SM (640 threads), warp-specialised:
-//   warp 0       TMA producer: codebook once (resident in shared memory), then one 128-pixel z tile per
-//                stage, loaded straight from NCHW (pixel-contiguous => MN-major A operand, no flatten copy)
-//   warp 1       MMA issuer: tcgen05.mma kind::tf32, M=128 pixels x N<=256 codes x K=8 per instruction,
-//                fp32 accumulators in TMEM (2 stages x 256 columns); one extra K-step multiplies a block of
-//                ones with a 3-way tf32 split of -|e|^2/2, so the accumulator holds z.e - |e|^2/2 directly
-//   warps 2,3    |z|^2 of the tile's pixels (bound of the tf32 error, last term of the exact score)
-//   warps 4..19  epilogue, warp = (TMEM lane quadrant, column group): thread = (pixel, quarter of the codes).
-//                scan: tcgen05.ld 32 columns at a time, running max (FMNMX3) and a sign-bit candidate mask
-//                against (max - bound) (FADD + SHF); the four column groups of a pixel merge their bounds
-//                through shared memory; pixels left with >1 candidate put (pixel, code) pairs on a per-quadrant
-//                work list that the quadrant's warps score in EXACT fp32 (reference op order), lanes over
-//                channels; then every thread gathers q, (z-q)^2 and the EMA statistics for a quarter of the
-//                channels of its pixel.
+// Two kernels, one persistent CTA per SM (640 threads, 227 KB shared memory, all 512 TMEM columns), warp-specialised:
 //
-// Exactness: tf32 drops 13 mantissa bits of z and e, so an approximate score can be off by at most
-//   b = 2^-8 |z| |e|  (+ accumulation slop).  Every code whose approximate score is within 2b of the
-//   approximate maximum is re-scored in exact fp32, so the winner is the fp32 winner.  Rows with more
-//   candidates than the kernel keeps, non-finite rows, or rows where a norm-outlier ("exploded") code could
-//   still win are appended to a list that a CUDA-core kernel then searches exhaustively.  Nothing is
-//   probabilistic.
+// vq_assign_tc_kernel  (codebook resident in shared memory: K*D*4 <= ~140 KB)
+//   warp 0       TMA producer: the norm-sorted codebook once, then one 128-pixel z tile per stage (2 stages), loaded
+//                straight from NCHW (pixel-contiguous => MN-major A operand, no flatten copy)
+//   warp 1       MMA issuer: tcgen05.mma kind::tf32, M=128 pixels x N<=256 codes x K=8 per instruction, fp32 accumulators
+//                in TMEM (2 stages x 256 columns); one extra K-step multiplies a block of ones with a 3-way tf32 split of
+//                the augmentation -|e|^2 / (2 (1 + 2^-10)), so the accumulator is the (centred) score
+//   warps 2,3    |z|^2 of the tile's pixels (bound of the tf32 error, last term of the exact score)
+//   warps 4..11  scan, warp = (TMEM lane quadrant, column group), thread = pixel: tcgen05.ld 32 columns at a time,
+//                running max (FMNMX3) and a sign-bit candidate mask against (max - bound); publishes
+//                {bounds, <= 2 candidate chunks + masks} per pixel to shared memory
+//   warps 12..19 output, lane = (pixel, channel-quad parity): z of the tile into registers (the stage goes back to the
+//                producer at once), merge of the column groups, exact fp32 re-rank of pixels with several candidates by
+//                the pixel's own two lanes, then ids, q, (z-q)^2, histogram and EMA sums
+// vq_assign_tcs_kernel (codebook streamed: D >= 128 at K = 512, K = 4096)
+//   one ring of (z chunk + codebook slice) stages, sixteen epilogue warps in two teams that each scan, merge, re-rank
+//   and write every other tile; z and the exact code rows of the output phase come from L2.
+//
+// Exactness: kind::tf32 TRUNCATES the fp32 operands (tools/trunc_check.py), so every product shrinks by a factor in
+//   (1 - 2^-9, 1]; with the factor (1 + 2^-10) folded into the augmentation an approximate score is off by at most
+//   delta = 2^-10 |z| |e| (+ accumulation slop).  Every code whose approximate score is within 2 delta of the approximate
+//   maximum is re-scored in exact fp32 (the reference's op order), so the winner is the fp32 winner.  Rows with more
+//   candidates than the kernel keeps, non-finite rows, or rows where a norm-outlier ("exploded") code could still win are
+//   appended to a list that a CUDA-core kernel then searches exhaustively.  Nothing is probabilistic.
 #include <cuda.h>
 #include <math.h>
 
