@@ -44,6 +44,7 @@ WORKLOADS = {
     "k4096d64": dict(B=16, D=64, H=256, K=4096),
     "k64d256": dict(B=16, D=256, H=256, K=64),
     "k4096d256": dict(B=16, D=256, H=256, K=4096),
+    "recon_k10d16": dict(B=16, D=16, H=512, K=10),          # run_recon.py:27-48 (LungConfig): K = 10, D = 16, 512 x 512 slices
 }
 METRIC = "vq_lookups_per_s"
 UNIT = "lookups/s"
@@ -385,7 +386,7 @@ def run_b200_arm(args, wl, wl_name):
                     traffic = tj["bytes"]
             except Exception:
                 traffic = None
-            roof.update({"traffic": traffic, "kernel": "vq_assign_tc" if path == 1 else "vq_assign_simt",
+            roof.update({"traffic": traffic, "kernel": {1: "vq_assign_tc", 2: "vq_assign_small"}.get(path, "vq_assign_simt"),
                          "kernel_ms": avg_kernel_ms, "launches_timed": nl.value,
                          "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                          "peak_source": f"MEASURED_PEAKS.json ({which})"})
@@ -394,7 +395,7 @@ def run_b200_arm(args, wl, wl_name):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl, wl_name, world, extra={"search_path": "tcgen05+fp32-rerank" if path == 1 else "fp32-cuda-core",
+            "config": workload_config(wl, wl_name, world, extra={"search_path": {1: "tcgen05+fp32-rerank", 2: "fp32-small-codebook"}.get(path, "fp32-cuda-core"),
                                                           "ema_state": "cold" if args.cold else "warmed",
                                                           "stats_exchange": ("none" if world == 1 else "inline" if args.inline_exchange
                                                                              else "packed all-reduce + EMA on a side stream")}),

@@ -38,6 +38,7 @@ typedef void* vq_stream_t;
 
 /* vq_assign_fwd flags */
 #define VQ_FLAG_FORCE_SIMT    1   /* use the exact fp32 CUDA-core search (no tensor cores)   */
+#define VQ_FLAG_NO_STATS      4   /* vq_assign_path only: the call will pass stats == NULL   */
 #define VQ_FLAG_FORCE_TC      2   /* fail instead of silently choosing the CUDA-core search */
 
 /* vq_lookup layouts */
@@ -52,8 +53,10 @@ int vq_version(void);
 /* Last error message of the calling thread ("" if none). */
 const char* vq_last_error(void);
 
-/* Which search kernel vq_assign_fwd would use for this shape: 0 = fp32 CUDA-core,
- * 1 = tcgen05 tensor-core + exact fp32 re-rank. */
+/* Which search kernel vq_assign_fwd would use for this shape: 0 = fp32 CUDA-core (register-tiled),
+ * 1 = tcgen05 tensor-core + exact fp32 re-rank, 2 = small-codebook fp32 kernel (inference calls, i.e. stats == NULL --
+ * tell vq_assign_path with VQ_FLAG_NO_STATS -- with K <= 16 and K*D <= 256: the reference's real dictionaries,
+ * run_recon.py:27-48). */
 int vq_assign_path(int B, int D, int H, int W, int K, int flags);
 
 /* Workspace bytes needed by vq_assign_fwd for N = B*H*W vectors. */

@@ -22,6 +22,7 @@ size_t vq_workspace_bytes(int64_t N, int K, int D) {
 
 int vq_assign_path(int B, int D, int H, int W, int K, int flags) {
   if (flags & VQ_FLAG_FORCE_SIMT) return 0;
+  if ((flags & VQ_FLAG_NO_STATS) && !(flags & VQ_FLAG_FORCE_TC) && small_path_supported(B, D, H, W, K)) return 2;
   return tc_path_supported(B, D, H, W, K) ? 1 : 0;
 }
 
@@ -48,7 +49,9 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
   a.ws = carve_workspace(workspace, N, K, D);
   cudaStream_t s = (cudaStream_t)stream;
 
-  bool use_tc = !(flags & VQ_FLAG_FORCE_SIMT) && q != nullptr && tc_path_supported(B, D, H, W, K);
+  const bool use_small = stats == nullptr && !(flags & (VQ_FLAG_FORCE_SIMT | VQ_FLAG_FORCE_TC)) &&
+                         small_path_supported(B, D, H, W, K);       // inference calls on small codebooks
+  bool use_tc = !use_small && !(flags & VQ_FLAG_FORCE_SIMT) && q != nullptr && tc_path_supported(B, D, H, W, K);
   if ((flags & VQ_FLAG_FORCE_TC) && !use_tc) {
     set_error("vq_assign_fwd: tensor-core path unsupported for B=%d D=%d H=%d W=%d K=%d", B, D, H, W, K);
     return VQ_ERR_UNSUPPORTED;
@@ -60,6 +63,9 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
       rc = launch_assign_tc(a, s);           // tcgen05 approximate search + exact fp32 re-rank
       if (rc) return rc;
       rc = launch_fallback_rows(a, s);       // exhaustive fp32 search of the rows the bound could not decide
+      if (rc) return rc;
+    } else if (use_small) {
+      rc = launch_assign_small(a, s);          // small codebooks: thread = pixel, exact fp32, HBM speed
       if (rc) return rc;
     } else {
       rc = launch_assign_simt(a, false, s);

@@ -104,6 +104,8 @@ struct FwdArgs {
 int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s);
 int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s);
 int launch_assign_tc(const FwdArgs& a, cudaStream_t s);          // vq_assign_tc.cu
+int launch_assign_small(const FwdArgs& a, cudaStream_t s);       // vq_assign_small.cu: K <= 32, K*D <= 1024
+bool small_path_supported(int B, int D, int H, int W, int K);    // vq_assign_small.cu
 bool tc_path_supported(int B, int D, int H, int W, int K);       // vq_assign_tc.cu
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int tc_debug_ncols(int D, int K);

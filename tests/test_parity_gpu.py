@@ -168,6 +168,36 @@ def test_multi_tile_vs_oracle(B, H, K, D, kind):
     assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
 
 
+# inference calls on small codebooks (K <= 16, K*D <= 256: run_recon's K = 10, D = 16) take the thread-per-pixel kernel
+SMALL_CODEBOOK = [(2, 64, 10, 16, "gauss"), (3, 40, 16, 16, "clustered"), (1, 50, 7, 12, "relu"), (5, 16, 3, 5, "gauss"),
+                  (2, 128, 10, 16, "clustered"), (1, 24, 1, 8, "gauss")]
+
+
+@pytest.mark.parametrize("B,H,K,D,kind", SMALL_CODEBOOK)
+def test_small_codebook_inference_vs_oracle_and_simt(B, H, K, D, kind):
+    z, embed = seeded_case(B, D, H, H, K, seed=977 + K + D + B, kind=kind)
+    assert pkg.lib().vq_assign_path(B, D, H, H, K, _native.VQ_FLAG_NO_STATS) == 2
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H, chunk=8192)
+    ora.eval()
+    q_ref, loss_ref, ids_ref = ora(z)
+    outs = []
+    for flags in (0, _native.VQ_FLAG_FORCE_SIMT):
+        m = new_vq(K, D, 0.99, flags)
+        set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+        m.eval()
+        zg = z.to(DEV).requires_grad_(True)
+        q, loss, ids = m(zg)
+        (gz,) = torch.autograd.grad(q.sum() + 0.5 * loss, zg)
+        outs.append((ids, q.detach(), loss.item(), gz))
+        assert torch.equal(m.embed.cpu(), ora.embed), "eval must not touch the buffers"
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "small-codebook kernel != CUDA-core search"
+    assert torch.equal(outs[0][3], outs[1][3])
+    nties = assert_ids_match(outs[0][0], ids_ref, embed, z)
+    if nties == 0:
+        assert torch.equal(outs[0][1].cpu(), q_ref.detach().contiguous())
+    assert abs(outs[0][2] - loss_ref.item()) <= TOL * abs(loss_ref.item())
+
+
 @pytest.mark.parametrize("flags", PATHS)
 def test_cold_start_exploded_codes(flags):
     """First EMA step with cluster_size == 0 blows unused codes up to ~1e5 x (SURVEY section 7);

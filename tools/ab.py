@@ -11,7 +11,7 @@ D = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 data = sys.argv[4] if len(sys.argv) > 4 else "noise"      # noise | clustered (z = code + 0.1 noise) | relu
-H = 256
+H = int(os.environ.get("ABH", 256))      # ABH=512: 512 x 512 slices
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(1)
 L = pkg.lib()
