@@ -625,6 +625,7 @@ vq_lookup_rows_kernel(const int64_t* __restrict__ ids, long long n, const float*
 
 // ids [B,A,C] -> out [B,D,C,A]: out[b,d,c,a] = E[ids[b,a,c]][d].  Tile: 32 a x 32 c per CTA so that
 // both the id reads (c fastest) and the output writes (a fastest) are coalesced.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, int K, int D,
                         float* __restrict__ out, int B, int A, int C, int* __restrict__ status) {
@@ -642,6 +643,29 @@ vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict
     sid[r][lx] = v;
   }
   __syncthreads();
+  if (VEC) {
+    // A % 4 == 0, out 16-byte aligned: thread = four consecutive a of one c, one streaming float4 store per channel
+    const int a4 = (threadIdx.x & 7) * 4, cc = threadIdx.x >> 3;
+    const int a = a0 + a4, c = c0 + cc;
+    if (a < A && c < C) {                 // A % 4 == 0: the quad is inside or outside as a whole
+      const int i0 = sid[a4][cc], i1 = sid[a4 + 1][cc], i2 = sid[a4 + 2][cc], i3 = sid[a4 + 3][cc];
+      const float* e0 = E + (size_t)(i0 < 0 ? 0 : i0) * D;
+      const float* e1 = E + (size_t)(i1 < 0 ? 0 : i1) * D;
+      const float* e2 = E + (size_t)(i2 < 0 ? 0 : i2) * D;
+      const float* e3 = E + (size_t)(i3 < 0 ? 0 : i3) * D;
+      float* o = out + (((long long)b * D) * C + c) * A + a;
+      const long long dstride = (long long)C * A;
+#pragma unroll 4
+      for (int d = 0; d < D; ++d) {
+        float4 v;
+        v.x = i0 < 0 ? 0.f : __ldg(e0 + d);
+        v.y = i1 < 0 ? 0.f : __ldg(e1 + d);
+        v.z = i2 < 0 ? 0.f : __ldg(e2 + d);
+        v.w = i3 < 0 ? 0.f : __ldg(e3 + d);
+        __stcs(reinterpret_cast<float4*>(o + d * dstride), v);
+      }
+    }
+  } else {
   // thread: a = a0 + lx (fastest in output), c = c0 + r
   for (int r = ly; r < 32; r += 8) {
     const int a = a0 + lx, c = c0 + r;
@@ -652,6 +676,7 @@ vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict
       const long long dstride = (long long)C * A;
       for (int d = 0; d < D; ++d) o[d * dstride] = (id < 0) ? 0.f : __ldg(e + d);
     }
+  }
   }
 }
 
@@ -811,7 +836,10 @@ int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int 
     vq_lookup_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(ids, n, embed, K, D, out, status);
   } else {
     dim3 grid((A + 31) / 32, (C + 31) / 32, B);
-    vq_lookup_nchw_t_kernel<<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+    if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0)
+      vq_lookup_nchw_t_kernel<true><<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+    else
+      vq_lookup_nchw_t_kernel<false><<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
   }
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
