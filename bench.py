@@ -15,7 +15,10 @@ One JSON line on stdout (rank 0).  `value` = whole-job lookups/s with inputs res
 `e2e` = the same through the module's public API with HOST (pinned) input and the result (loss +
 code map) read back every step; `roofline` = the dominant kernel (nearest-code search) against the
 measured HBM peak; `cpu_baseline` = the oracle (a port of the reference's torch op chain) on the
-host cores, bounded sample.
+host cores, bounded sample.  `vqwnet_train` = the other half of BASELINE's metric: VQ-W-Net training slices/s
+(BASELINE config 2: batch 16 of 256x256 slices per GPU, tools/wnet.py around this repo's quantiser, stock cuDNN
+convolutions, Adam), device-resident and end-to-end, measured after the headline region; `--workload vqwnet`
+makes it the line's own metric (and `--impl reference --workload vqwnet` times the same network on the host cores).
 """
 from __future__ import annotations
 
@@ -361,6 +364,17 @@ def run_b200_arm(args, wl, wl_name):
                 fb_rows = int(L.vq_debug_fallback_rows(wsb.data_ptr(), n_per_gpu, K, D, torch.cuda.current_stream().cuda_stream))
     vq.train(True)
 
+    # ---- the other half of BASELINE's metric: VQ-W-Net train slices/s (after, and outside, the headline regions) ----
+    wnet = None
+    if wl_name == "config2" and not args.no_model:
+        try:
+            wnet = measure_wnet_b200(dev, rank, world, steps=max(3, min(args.steps, 10)), warmup=3,
+                                     inline_exchange=args.inline_exchange)
+        except Exception as exc:                                 # never lose the headline line to the model leg
+            if world > 1:
+                raise
+            wnet = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         hbm, bf16, which = measured_peaks()
         total_lookups = world * n_per_gpu * args.steps
@@ -409,7 +423,207 @@ def run_b200_arm(args, wl, wl_name):
             "cpu_baseline": cpu,
             "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms,
                              "fallback_rows": fb_rows},
+            "vqwnet_train": wnet,
         }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# VQ-W-Net training step (BASELINE config 2 / 5): the hot path inside its caller
+# ---------------------------------------------------------------------------------------------
+WNET = dict(B=16, H=256, K=512, D=64, lr=1e-4, commit_weight=1.0)
+WNET_METRIC = "vqwnet_train_slices_per_s"
+WNET_UNIT = "slices/s"
+
+
+def wnet_config(gpus, extra=None):
+    c = {"workload": f"vqwnet: VQ-W-Net training step (tools/wnet.py = vqwnet.py topology, filters 64..1024, K = {WNET['K']}; "
+                     f"loss = mse(recon, x) + commit_loss, Adam lr 1e-4), batch {WNET['B']} of 1x{WNET['H']}x{WNET['H']} "
+                     "synthetic slices per GPU, fp32 (cuDNN convolutions at torch's default: TF32 allowed)",
+         "slices_per_gpu": WNET["B"], "resolution": WNET["H"], "dict_size": WNET["K"], "emb_dim": WNET["D"],
+         "parallelism": f"dp{gpus}", "l2": "a step streams > 10 GB of activations (>> 126 MB L2)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def wnet_images(n, B, H, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    out = [torch.randn(B, 1, H, H, generator=g).clamp_(-1, 1) for _ in range(n)]
+    return [t.pin_memory() for t in out] if pin else out
+
+
+def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
+    """VQ-W-Net train slices/s on this rank's GPU (data parallel over `world` ranks).  Returns a dict on rank 0."""
+    import torch.distributed as dist
+    import medical_image_editing_b200 as pkg
+    from medical_image_editing_b200.src.trainers.ddp import DataParallelVQTrainer
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from wnet import WNetHarness
+
+    L = pkg.lib()
+    B, H = WNET["B"], WNET["H"]
+    torch.manual_seed(0)
+    model = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch",
+                                            overlap_exchange=(world > 1 and not inline_exchange)),
+                        1, dict_size=WNET["K"]).to(dev)
+    trainer = DataParallelVQTrainer(model, lr=WNET["lr"], commit_weight=WNET["commit_weight"])
+    host = wnet_images(4, B, H, 4321 + rank, pin=True)
+    resident = [t.to(dev) for t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxed(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(warmup):
+        trainer.training_step(resident[i % 4])
+    barrier()
+    L.vq_profile_enable(1)
+    L.vq_profile_read(None, None)
+    launches0 = L.vq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        trainer.training_step(resident[i % 4])
+    e1.record()
+    barrier()
+    ms = maxed(e0.elapsed_time(e1))
+    launches = L.vq_launch_count() - launches0
+    tot_ms, nl = ctypes.c_double(0), ctypes.c_int(0)
+    L.vq_profile_read(ctypes.byref(tot_ms), ctypes.byref(nl))
+    L.vq_profile_enable(0)
+
+    # end to end: each step's images come from pinned host memory, the loss is read back by the host
+    dev_in = torch.empty(B, 1, H, H, device=dev)
+    losses = []
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(steps):
+        dev_in.copy_(host[i % 4], non_blocking=True)
+        out = trainer.training_step(dev_in)
+        losses.append(float(out["loss"].item()))
+    s1.record()
+    barrier()
+    e2e_ms = maxed(s0.elapsed_time(s1))
+    in_sync = trainer.replicas_in_sync()
+    del trainer, model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    hbm, _, which = measured_peaks()
+    n_vec = B * H * H
+    alg_bytes = n_vec * (8 * WNET["D"] + 8)
+    k_ms = (tot_ms.value / nl.value) if nl.value else None
+    return {
+        "metric": WNET_METRIC, "value": world * B * steps / (ms * 1e-3), "unit": WNET_UNIT, "ms_per_step": ms / steps,
+        "steps": steps, "warmup": warmup, "n_gpus": world,
+        "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": WNET_UNIT, "h2d_bytes_per_step": B * H * H * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
+        "gpu_launches": int(launches),
+        "quantiser_search_kernel_ms": k_ms,
+        "roofline": (None if not k_ms else {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                            "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel": "vq_assign_tc",
+                                            "peak_source": f"MEASURED_PEAKS.json ({which})"}),
+        "replicas_in_sync": bool(in_sync), "final_loss": losses[-1] if losses else None,
+    }
+
+
+def cpu_wnet_step_factory(slices):
+    from oracle.vq_oracle import OracleVQ
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from wnet import WNetHarness
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = WNetHarness(lambda d, k: OracleVQ(d, k, 0.99, 1e-5, "torch", chunk=65536), 1, dict_size=WNET["K"])
+    model.train(True)
+    opt = torch.optim.Adam(model.parameters(), lr=WNET["lr"])
+    imgs = wnet_images(2, slices, WNET["H"], 4321)
+    state = {"i": 0}
+
+    def step():
+        x = imgs[state["i"] % 2]
+        state["i"] += 1
+        opt.zero_grad(set_to_none=True)
+        out = model(x)
+        loss = torch.nn.functional.mse_loss(out["recon"], x) + WNET["commit_weight"] * out["commit_loss"]
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step
+
+
+def run_cpu_wnet_baseline(budget_s=15.0, slices=1):
+    step = cpu_wnet_step_factory(slices)
+    step()
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < 2 or (time.perf_counter() - t_all < budget_s and len(times) < 20):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": slices / med, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{slices} slice(s) per step: tools/wnet.py with the CPU oracle quantiser (bit-identical to the reference "
+                      f"VQWNet on CPU, tests/test_wnet_harness.py), median of {len(times)} steps, {med * 1e3:.0f} ms/step"}
+
+
+def run_wnet_reference_arm(args):
+    if env_int("RANK", 0) != 0:
+        return
+    os.environ["WORLD_SIZE"] = "1"
+    slices = 1
+    step = cpu_wnet_step_factory(slices)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = slices * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": WNET_METRIC, "value": val, "unit": WNET_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": wnet_config(args.gpus, extra={"reference_sample_slices_per_step": slices}),
+        "cpu_baseline": {"value": val, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{slices} slice per step; VQ-W-Net topology with the oracle quantiser on the host cores"},
+        "e2e": {"value": val, "unit": WNET_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_wnet_b200_arm(args):
+    import torch.distributed as dist
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the quantiser has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    r = measure_wnet_b200(dev, rank, world, args.steps, args.warmup, args.inline_exchange)
+    t1 = time.time()
+    if rank == 0:
+        clocks = sampler.stop(t0, t1)
+        cpu = run_cpu_wnet_baseline() if (world == 1 and not args.no_cpu) else None
+        out = {"metric": WNET_METRIC, "value": r["value"], "unit": WNET_UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wnet_config(world),
+               "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": r["roofline"],
+               "cpu_baseline": cpu, "replicas_in_sync": r["replicas_in_sync"], "final_loss": r["final_loss"]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -421,13 +635,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["vqwnet"])
+    ap.add_argument("--no-model", action="store_true", help="skip the VQ-W-Net train slices/s block of the default line")
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
     ap.add_argument("--inline-exchange", action="store_true", help="N > 1: all-reduce + EMA update on the compute stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "vqwnet":
+        return run_wnet_reference_arm(args) if args.impl == "reference" else run_wnet_b200_arm(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl, args.workload)
