@@ -40,6 +40,9 @@ typedef void* vq_stream_t;
 #define VQ_FLAG_FORCE_SIMT    1   /* use the exact fp32 CUDA-core search (no tensor cores)   */
 #define VQ_FLAG_NO_STATS      4   /* vq_assign_path only: the call will pass stats == NULL   */
 #define VQ_FLAG_FORCE_TC      2   /* fail instead of silently choosing the CUDA-core search */
+#define VQ_FLAG_PAIR          8   /* streamed-codebook tensor-core kernel: 2-CTA clusters (cta_group::2, each CTA holds
+                                     half of every codebook slice) instead of one CTA per tile; same results, not
+                                     faster on B200 -- kept for A/B timing */
 
 /* vq_lookup layouts */
 #define VQ_LAYOUT_ROWS        0   /* out[n, D]  (F.embedding layout, vq_module.py:203-206)  */

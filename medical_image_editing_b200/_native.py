@@ -18,6 +18,7 @@ c_i32p = ctypes.c_void_p
 VQ_FLAG_FORCE_SIMT = 1
 VQ_FLAG_FORCE_TC = 2
 VQ_FLAG_NO_STATS = 4
+VQ_FLAG_PAIR = 8
 VQ_LAYOUT_ROWS = 0
 VQ_LAYOUT_NCHW_T = 1
 

@@ -27,6 +27,8 @@
 //   appended to a list that a CUDA-core kernel then searches exhaustively.  Nothing is probabilistic.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "vq_common.cuh"
 
@@ -234,6 +236,84 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- q leaves through the TMA: a [16 pixel x 32 channel] box staged in shared memory per warp
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster share one M = 256 MMA; loads of both CTAs signal the
+// leader's (cluster rank 0) barrier, tcgen05.commit arrives on the same barrier slot of both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_idx() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_addr) {      // same offset in the shared memory of cluster rank 0
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(local_bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep_cluster(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+  }
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_pair(int n) {           // as make_idesc, M = 256 over the two CTAs
+  return (make_idesc(n) & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -985,17 +1065,21 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 // the exact fp32 code rows from global memory (both L2 hits: the tile and the codebook were just streamed).
 struct TcsGeom {
   int BN, nb, nD, nst;
-  size_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_bar, total;
+  size_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_qst, off_bar, total;
   bool ok;
 };
+constexpr int TCS_QST_BYTES = 16 * TC_DCH * 4;      // q staging box of one epilogue warp: 16 pixels x 32 channels
 constexpr int TCS_MAX_ND = 8;       // D <= 256
 constexpr int TCS_MAX_ST = 8;       // ring stages
 constexpr int TCS_MAXCAND = 16;     // candidates re-scored exactly per pixel (large codebooks tie more often)
 // barrier slots of the streaming kernel
 constexpr int TCS_B_FULL = 0, TCS_B_EMPTY = 8, TCS_B_AFULL = 16, TCS_B_AEMPTY = 18, TCS_B_TFULL = 20, TCS_B_TEMPTY = 22,
-              TCS_B_ZN = 24, TCS_B_TMEM = 30;
+              TCS_B_ZN = 24, TCS_B_TMEM = 30, TCS_B_CONS = 32;
 
-static TcsGeom tcs_geometry(int D, int K) {
+// pair = CTA-pair mode (cta_group::2, BN = 256 only): each CTA of a 2-CTA cluster keeps its own 128-pixel z chunk but
+// only HALF of every codebook slice (the tensor cores of both SMs read both halves), so the codebook crosses
+// L2 -> SM once per 256 pixels instead of once per 128
+static TcsGeom tcs_geometry(int D, int K, bool pair = false) {
   TcsGeom g{};
   g.ok = false;
   g.BN = 32;
@@ -1003,14 +1087,17 @@ static TcsGeom tcs_geometry(int D, int K) {
   g.nb = (K + g.BN - 1) / g.BN;
   g.nD = (D + TC_DCH - 1) / TC_DCH;
   if (g.nD > TCS_MAX_ND || g.nb * g.BN > TC_SORT_MAX) return g;
-  g.stage_bytes = (size_t)TC_TILE * 128 + (size_t)g.BN * 128;          // z chunk + codebook slice (both 1024-aligned)
+  if (pair && g.BN != TC_MAXBN) return g;
+  const int bmine = pair ? g.BN / 2 : g.BN;                             // codes of a slice held by this CTA
+  g.stage_bytes = (size_t)TC_TILE * 128 + (size_t)bmine * 128;         // z chunk + codebook slice (both 1024-aligned)
   size_t off = 0;
-  g.off_aug = off;  off += align_up((size_t)2 * g.BN * 32, 1024);
+  g.off_aug = off;  off += align_up((size_t)2 * bmine * 32, 1024);
   g.off_aaug = off; off += 4096;
   g.off_stage = off;
   const size_t sz_pub = (size_t)4 * TC_NCG * TC_TILE * 16, sz_zn = 2 * TC_TILE * 4;   // pub: [team][tile parity][column group][pixel]
   const size_t sz_ctab = align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
-  const size_t tail = sz_pub + sz_zn + sz_ctab + 512;
+  const size_t sz_qst = (size_t)(TC_SCAN_WARPS + TC_OUT_WARPS) * TCS_QST_BYTES;
+  const size_t tail = sz_pub + sz_zn + align_up(sz_ctab, 128) + sz_qst + 512;
   long long room = (long long)TC_SMEM_LIMIT - 1024 - (long long)off - (long long)tail;
   int nst = (int)(room / (long long)g.stage_bytes);
   if (nst > TCS_MAX_ST) nst = TCS_MAX_ST;
@@ -1024,7 +1111,8 @@ static TcsGeom tcs_geometry(int D, int K) {
   off += (size_t)nst * g.stage_bytes;
   g.off_pub = off;  off += sz_pub;
   g.off_zn = off;   off += sz_zn;
-  g.off_ctab = off; off += sz_ctab;
+  g.off_ctab = off; off += align_up(sz_ctab, 128);
+  g.off_qst = off;  off += sz_qst;
   g.off_bar = off;  off += 512;
   g.total = off + 1024;
   g.ok = true;
@@ -1038,16 +1126,17 @@ struct TcsParams {
   int BN, nb, nD, nst;
   int bn_shift, w_shift;
   int tiles_per_img; int ntiles;
-  uint32_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_bar;
+  uint32_t stage_bytes, off_stage, off_aug, off_aaug, off_pub, off_zn, off_ctab, off_qst, off_bar;
   int64_t* ids; int32_t* ids_nat; float* q; double* loss_acc; int* counts;
   float* sums; float* sums_rep; int nrep;
   int* fb_count; int* fb_rows;
   float* dbg;
 };
 
-template <bool DBG, bool STATS>
+template <bool DBG, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const TcsParams P) {
+vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap,
+                     const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap qmap, const TcsParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -1059,19 +1148,34 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
   const int nD = P.nD, nst = P.nst;
   const int ktot = P.nb * P.BN;
   const uint32_t stage_bytes = P.stage_bytes;                 // z chunk (16 KB) followed by the codebook slice
+  // CTA pair: rank 0 (the leader) issues the M = 256 MMAs for both CTAs; work unit = a pair of adjacent tiles
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)cluster_idx() : (int)blockIdx.x;
+  const int ustride = PAIR ? (int)cluster_count() : (int)gridDim.x;
+  const int nunits = PAIR ? (P.ntiles + 1) >> 1 : P.ntiles;
+  const int bmine = PAIR ? P.BN >> 1 : P.BN;                   // codes of every slice held in this CTA's shared memory
 
   if (threadIdx.x == 32) {
-    for (int i = 0; i < TCS_MAX_ST; ++i) { mbar_init(BAR(TCS_B_FULL + i), 1); mbar_init(BAR(TCS_B_EMPTY + i), 3); }   // MMA commit + |z|^2 warps
+    // single CTA: a stage is released by the MMA commit + the two |z|^2 warps.  Pair: the commit arrives on CONS (both
+    // CTAs), the |z|^2 warps wait for it (the peer CTA never sees the leader's FULL barrier) and release the stage.
+    for (int i = 0; i < TCS_MAX_ST; ++i) {
+      mbar_init(BAR(TCS_B_FULL + i), 1); mbar_init(BAR(TCS_B_EMPTY + i), PAIR ? 2 : 3); mbar_init(BAR(TCS_B_CONS + i), 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(TCS_B_AFULL + i), 1); mbar_init(BAR(TCS_B_AEMPTY + i), 1);
-      mbar_init(BAR(TCS_B_TFULL + i), 1); mbar_init(BAR(TCS_B_TEMPTY + i), TC_SCAN_WARPS);
+      mbar_init(BAR(TCS_B_TFULL + i), 1); mbar_init(BAR(TCS_B_TEMPTY + i), PAIR ? 2 * TC_SCAN_WARPS : TC_SCAN_WARPS);
       mbar_init(BAR(TCS_B_ZN + i), 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (warp >= TC_AUX_WARPS) {
     const int t = threadIdx.x - 32 * TC_AUX_WARPS;
@@ -1092,48 +1196,70 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();               // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = (nunits - unit0 + ustride - 1) / ustride;        // work units (tiles, or tile pairs) of this CTA
+  // tile of my it-th unit; in pair mode the odd CTA of the last pair may get a phantom tile (>= ntiles): it is loaded
+  // (out-of-range boxes are zero-filled) and scanned like any other, and produces no output
+  auto tile_of = [&](int it) { return PAIR ? 2 * (unit0 + it * ustride) + (int)crank : unit0 + it * ustride; };
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int scount = 0, acount = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = tile_of(it);
         const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
         for (int blk = 0; blk < P.nb; ++blk) {
           {   // this block's -|e|^2/2 image
             const int as = acount & 1;
             mbar_wait_sleep(BAR(TCS_B_AEMPTY + as), ((acount >> 1) & 1) ^ 1, 64);
-            mbar_expect_tx(BAR(TCS_B_AFULL + as), (uint32_t)P.BN * 32);
-            bulk_load_1d(sbase + P.off_aug + (uint32_t)as * P.BN * 32, P.eaug_img + (size_t)blk * P.BN * 8, (uint32_t)P.BN * 32,
-                         BAR(TCS_B_AFULL + as));
+            if (PAIR) {      // both halves are counted on the leader's barrier
+              if (crank == 0) mbar_expect_tx(BAR(TCS_B_AFULL + as), (uint32_t)P.BN * 32);
+              tma_load_2d_pair(sbase + P.off_aug + (uint32_t)as * bmine * 32, &amap, leader_addr(BAR(TCS_B_AFULL + as)), 0,
+                               (blk * P.BN + (int)crank * bmine) >> 3);
+            } else {
+              mbar_expect_tx(BAR(TCS_B_AFULL + as), (uint32_t)P.BN * 32);
+              bulk_load_1d(sbase + P.off_aug + (uint32_t)as * P.BN * 32, P.eaug_img + (size_t)blk * P.BN * 8, (uint32_t)P.BN * 32,
+                           BAR(TCS_B_AFULL + as));
+            }
             ++acount;
           }
           for (int c = 0; c < nD; ++c, ++scount) {
             const int st = scount % nst;
             mbar_wait_sleep(BAR(TCS_B_EMPTY + st), ((scount / nst) & 1) ^ 1, 32);
-            mbar_expect_tx(BAR(TCS_B_FULL + st), stage_bytes);
             const uint32_t dst = sbase + P.off_stage + (uint32_t)st * stage_bytes;
-            for (int grp = 0; grp < 4; ++grp)             // z chunk: four 32-pixel x 32-channel boxes
-              tma_load_3d(dst + grp * 4096, &zmap, BAR(TCS_B_FULL + st), pt * TC_TILE + grp * 32, c * TC_DCH, b);
-            tma_load_2d(dst + TC_TILE * 128, &emap, BAR(TCS_B_FULL + st), c * TC_DCH, blk * P.BN);
+            if (PAIR) {
+              if (crank == 0) mbar_expect_tx(BAR(TCS_B_FULL + st), 2u * stage_bytes);     // my stage and the peer's
+              const uint32_t fb = leader_addr(BAR(TCS_B_FULL + st));
+              for (int grp = 0; grp < 4; ++grp)
+                tma_load_3d_pair(dst + grp * 4096, &zmap, fb, pt * TC_TILE + grp * 32, c * TC_DCH, b);
+              tma_load_2d_pair(dst + TC_TILE * 128, &emap, fb, c * TC_DCH, blk * P.BN + (int)crank * bmine);
+            } else {
+              mbar_expect_tx(BAR(TCS_B_FULL + st), stage_bytes);
+              for (int grp = 0; grp < 4; ++grp)             // z chunk: four 32-pixel x 32-channel boxes
+                tma_load_3d(dst + grp * 4096, &zmap, BAR(TCS_B_FULL + st), pt * TC_TILE + grp * 32, c * TC_DCH, b);
+              tma_load_2d(dst + TC_TILE * 128, &emap, BAR(TCS_B_FULL + st), c * TC_DCH, blk * P.BN);
+            }
           }
         }
+      }
+      if (PAIR) {     // the leader's last commits arrive on this CTA's AEMPTY barriers: let them land before the CTA exits
+        for (int k = acount > 2 ? acount - 2 : 0; k < acount; ++k) mbar_wait_sleep(BAR(TCS_B_AEMPTY + (k & 1)), (k >> 1) & 1, 64);
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(P.BN);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = PAIR ? make_idesc_pair(P.BN) : make_idesc(P.BN);
       int g = 0, scount = 0, acount = 0;
       for (int it = 0; it < my_tiles; ++it) {
         for (int blk = 0; blk < P.nb; ++blk, ++g) {
           const int a = g & 1, aph = (g >> 1) & 1;
-          mbar_wait_sleep(BAR(TCS_B_TEMPTY + a), aph ^ 1, 32);
+          if (PAIR) mbar_wait_sleep_cluster(BAR(TCS_B_TEMPTY + a), aph ^ 1, 32);       // scan warps of both CTAs
+          else mbar_wait_sleep(BAR(TCS_B_TEMPTY + a), aph ^ 1, 32);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
           uint32_t acc = 0;
@@ -1147,22 +1273,25 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t ad = make_desc(zaddr + ks * 1024, 4096, 512, 1);
               const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
-              umma_tf32(d_tmem, ad, bd, idesc, acc);
+              if (PAIR) umma_tf32_pair(d_tmem, ad, bd, idesc, acc);
+              else umma_tf32(d_tmem, ad, bd, idesc, acc);
               acc = 1;
             }
-            umma_commit(BAR(TCS_B_EMPTY + st));            // stage consumed by the tensor core
+            if (PAIR) umma_commit_pair(BAR(TCS_B_CONS + st));
+            else umma_commit(BAR(TCS_B_EMPTY + st));       // stage consumed by the tensor core
           }
           {
             const int as = acount & 1;
             mbar_wait_sleep(BAR(TCS_B_AFULL + as), (acount >> 1) & 1, 32);
             tc_fence_after();
             const uint64_t ad = make_desc(sbase + P.off_aaug, 1024, 512, 1);
-            const uint64_t bd = make_desc(sbase + P.off_aug + (uint32_t)as * P.BN * 32, 128, 256, 0);
-            umma_tf32(d_tmem, ad, bd, idesc, acc);
-            umma_commit(BAR(TCS_B_AEMPTY + as));
+            const uint64_t bd = make_desc(sbase + P.off_aug + (uint32_t)as * bmine * 32, 128, 256, 0);
+            if (PAIR) { umma_tf32_pair(d_tmem, ad, bd, idesc, acc); umma_commit_pair(BAR(TCS_B_AEMPTY + as)); }
+            else { umma_tf32(d_tmem, ad, bd, idesc, acc); umma_commit(BAR(TCS_B_AEMPTY + as)); }
             ++acount;
           }
-          umma_commit(BAR(TCS_B_TFULL + a));
+          if (PAIR) umma_commit_pair(BAR(TCS_B_TFULL + a));
+          else umma_commit(BAR(TCS_B_TFULL + a));
         }
       }
     }
@@ -1183,7 +1312,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           const int st = scount % nst;
           // always wait for the fill: an arrival may only count for the phase it belongs to (the producer refills a
           // stage after the previous phase of its EMPTY barrier completed)
-          mbar_wait(BAR(TCS_B_FULL + st), (scount / nst) & 1);
+          mbar_wait(BAR((PAIR ? TCS_B_CONS : TCS_B_FULL) + st), (scount / nst) & 1);
           if (blk == 0) {
             const uint32_t zc = zrow0 + (uint32_t)st * stage_bytes;
 #pragma unroll
@@ -1217,6 +1346,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     const int p = quad * 32 + lane;                       // scan: pixel within the tile == TMEM lane
     const uint32_t ctab_s = sbase + P.off_ctab;
     const uint32_t zn_s = sbase + P.off_zn + (uint32_t)(team * TC_TILE + p) * 4;
+    const uint32_t qst_s = sbase + P.off_qst + (uint32_t)ew * TCS_QST_BYTES;
     const int nchunks = P.BN >> 5;
     // output phase: lane = (pixel px, quad parity hf) of the 16 pixels quad*32 + cg*16 .. +15
     const int px = lane & (TC_OPX - 1), hf = lane >> TC_OPX_SHIFT;
@@ -1233,7 +1363,8 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
     float2 ls2 = make_float2(0.f, 0.f);
     TC_TIMING_DECL
     for (int it = team; it < my_tiles; it += 2) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_of(it);
+      const bool phantom = PAIR && tile >= P.ntiles;
       const int b = tile / P.tiles_per_img, p0 = (tile % P.tiles_per_img) * TC_TILE;
       const int n2 = it >> 1;                             // this team's tile counter
       TC_TICK(5);
@@ -1261,7 +1392,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cA), "=f"(cB) : "r"(ctab_s + (uint32_t)gc * 8));
           const float delta = __fmaf_rn(zn_scan, cA, cB);
           tmem_ld_wait();
-          if (DBG) {
+          if (DBG && !phantom) {
             float* o = P.dbg + ((size_t)b * P.HW + p0 + p) * ktot + gc * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = v[j];
@@ -1301,7 +1432,10 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(TCS_B_TEMPTY + a));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(BAR(TCS_B_TEMPTY + a));        // the leader's MMA warp waits for both CTAs' scans
+          else mbar_arrive(BAR(TCS_B_TEMPTY + a));
+        }
       }
       // ---- publish to the team: {L, U16 | chunkA<<8 | chunkB<<1 | overflow, maskA, maskB}, double-buffered by tile parity
       if (cnt < 2) rm1 = 0;
@@ -1315,6 +1449,7 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
       // team mate (it needs the mate's arrival at the next barrier), so two publication buffers per team are enough.
       if (team == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (phantom) continue;                               // (warp-uniform) nothing to write for a tile past the end
 
       // ---- merge the column groups of my output pixel ---------------------------------------------------------
       const float z2 = __shfl_sync(0xffffffffu, z2s, cg * TC_OPX + px);     // scan lane (pixel po) of this very warp
@@ -1413,13 +1548,18 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
 
       TC_TICK(4);
       // ---- outputs ------------------------------------------------------------------------------------
-      if (fb) {
-        if (hf == 0) {
+      // q does not leave through the load/store unit: with scalar q stores the LSU data pipe was 91 % busy (ncu,
+      // profiles/r01e_*), two fifths of it those stores (a global store costs the pipe two passes per 32-byte sector).
+      // Each warp stages the [16 pixel x 32 channel] box of one loop iteration in shared memory (one st.shared per
+      // value) and one lane hands it to the TMA (cp.async.bulk.tensor store).  Pixels left to the exhaustive fallback
+      // leave stale bytes in the box; the fallback kernel runs afterwards and rewrites them.
+      // Ablation hooks (tools/build_variant.sh abl -DVQ_ABL_TCS_NOOUT | _NOZ | _NOE): the phase without its loop / its z
+      // loads / its code-row gathers, to time what the rest of the kernel costs.
+      if (hf == 0) {
+        if (fb) {
           const int slot = atomicAdd(P.fb_count, 1);
           P.fb_rows[slot] = b * P.HW + pp;
-        }
-      } else {
-        if (hf == 0) {
+        } else {
           int h, wc;
           if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
           else { h = pp / P.W; wc = pp - h * P.W; }
@@ -1428,43 +1568,73 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           if (P.ids_nat) P.ids_nat[nb_ + pp] = worig;
           if (STATS) atomicAdd(&P.counts[worig], 1);
         }
-        const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)worig * D);
-        float* qo = P.q + (size_t)b * img_stride + pp;
-        float* so = STATS ? sums_mine + (size_t)worig * D : nullptr;
-        for (int j0 = hf; j0 < nq; j0 += 8) {             // my quads j = j0 + 2t: all loads of four quads first
+      }
+      {
+        const bool live = !fb;
+        const bool qout = !DBG || P.q;
+        const float4* er = reinterpret_cast<const float4*>(P.E + (size_t)(live ? worig : 0) * D);
+        float* so = STATS ? sums_mine + (size_t)(live ? worig : 0) * D : nullptr;
+        const uint32_t qs_lane = qst_s + (uint32_t)hf * (4 * 64) + (uint32_t)px * 4;      // + t * 512 + i * 64
+#ifdef VQ_ABL_TCS_NOOUT
+        for (int jc = 0; jc < 0; jc += 8) {
+#else
+        for (int jc = 0; jc < nq; jc += 8) {              // one 32-channel chunk per iteration (warp-uniform trip count:
+#endif
+          const int j0 = jc + hf;                         // the loop synchronises the warp); my quads j = j0 + 2t
           float4 e4[4];
           float zv[4][4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int j = j0 + 2 * t;
-            const bool in = j < nq;
+            const bool in = live && j < nq;
+#ifdef VQ_ABL_TCS_NOE
+            e4[t] = make_float4(1.f, 2.f, 3.f, (float)j);
+#else
             e4[t] = in ? __ldg(er + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
             const float* zj = zp + (size_t)(4 * j) * hw;
+#ifdef VQ_ABL_TCS_NOZ
+            zv[t][0] = zv[t][1] = zv[t][2] = zv[t][3] = (float)j;
+#else
             zv[t][0] = in ? __ldg(zj) : 0.f;          zv[t][1] = in ? __ldg(zj + hw) : 0.f;
             zv[t][2] = in ? __ldg(zj + 2 * hw) : 0.f; zv[t][3] = in ? __ldg(zj + 3 * hw) : 0.f;
+#endif
+          }
+          if (qout) {                                     // the TMA has read the previous box out of the staging buffer
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int j = j0 + 2 * t;
-            if (j < nq) {
+            if (live && j < nq) {
               const float2 m1 = make_float2(-1.f, -1.f);
               const float2 d01 = __ffma2_rn(make_float2(e4[t].x, e4[t].y), m1, make_float2(zv[t][0], zv[t][1]));
               const float2 d23 = __ffma2_rn(make_float2(e4[t].z, e4[t].w), m1, make_float2(zv[t][2], zv[t][3]));
               ls2 = __ffma2_rn(d01, d01, ls2);
               ls2 = __ffma2_rn(d23, d23, ls2);
-              if (!DBG || P.q) {
-                float* qj = qo + (size_t)(4 * j) * hw;
-                __stcs(qj, e4[t].x);
-                __stcs(qj + hw, e4[t].y);
-                __stcs(qj + 2 * hw, e4[t].z);
-                __stcs(qj + 3 * hw, e4[t].w);
+              if (qout) {                                 // box row = channel within the chunk: 4 (2t + hf) + i, 64 bytes per row
+                const uint32_t qa = qs_lane + (uint32_t)t * 512;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(qa), "f"(e4[t].x) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(qa + 64), "f"(e4[t].y) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(qa + 128), "f"(e4[t].z) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(qa + 192), "f"(e4[t].w) : "memory");
               }
               if (STATS) atomicAdd(reinterpret_cast<float4*>(so + 4 * j), make_float4(zv[t][0], zv[t][1], zv[t][2], zv[t][3]));
+            }
+          }
+          if (qout) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&qmap, qst_s, p0 + quad * 32 + cg * TC_OPX, (j0 >> 3) * TC_DCH, b);
+              bulk_commit();
             }
           }
         }
       }
     }
+    if (lane == 0) bulk_wait0();                          // every q box has landed before the CTA retires
     TC_TICK(5);
     TC_TIMING_STORE(ew, my_tiles);
     float lsum = ls2.x + ls2.y;
@@ -1473,9 +1643,11 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();               // neither CTA may leave (or free TMEM) while the pair's MMAs can touch it
+  else __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -1603,16 +1775,29 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   return VQ_OK;
 }
 
+// CTA-pair mode of the streamed kernel (256-wide code blocks, at least two tiles).  Opt-in: VQ_FLAG_PAIR, or VQ_TCS_PAIR=1
+// in the environment for A/B timing -- measured on B200 it is bit-identical to and no faster than one CTA per tile
+// (DESIGN.md 4.2), because the streamed kernel is not bound by the codebook's L2 -> SM traffic.
+static bool tcs_use_pair(const FwdArgs& a) {
+  static int env_on = -1;
+  if (env_on < 0) { const char* e = getenv("VQ_TCS_PAIR"); env_on = (e && e[0] == '1') ? 1 : 0; }
+  if (!env_on && !(a.flags & VQ_FLAG_PAIR)) return false;
+  const long long ntiles = (long long)a.B * (a.H * a.W / TC_TILE);
+  return ntiles >= 2 && sm_count_tc() >= 2 && tcs_geometry(a.D, a.K, true).ok;
+}
+
 static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
-  const TcsGeom g = tcs_geometry(a.D, a.K);
+  const bool pair = tcs_use_pair(a);
+  const TcsGeom g = tcs_geometry(a.D, a.K, pair);
   VQ_REQUIRE(g.ok && HW % TC_TILE == 0 && a.D % 4 == 0, VQ_ERR_UNSUPPORTED, "tensor-core path (streamed codebook): unsupported shape");
   VQ_REQUIRE(a.q != nullptr || dbg != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
   EncodeTiledFn enc = get_encode_fn();
   VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0, VQ_ERR_INVALID_ARG,
              "tensor-core path: z / embed must be 16-byte aligned");
-  CUtensorMap zmap, emap;
+  CUtensorMap zmap, emap, amap, qmap;
+  float* eaug_img = a.ws.tc_aug;
   {
     cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.D, (cuuint64_t)a.B};
     cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
@@ -1623,17 +1808,40 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
   }
-  {
+  {   // pair mode: a box is this CTA's half of a 256-code slice
     cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)(g.nb * g.BN)};
     cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
-    cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
+    cuuint32_t box[2] = {TC_DCH, (cuuint32_t)(pair ? g.BN / 2 : g.BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
   }
-  float* eaug_img = a.ws.tc_aug;
+  if (a.q) {   // q [B][D][HW] like z; a box is one epilogue warp's 16 pixels x one 32-channel chunk (dense rows of 64 bytes)
+    VQ_REQUIRE((((uintptr_t)a.q) & 15) == 0, VQ_ERR_INVALID_ARG, "tensor-core path: q must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
+    cuuint32_t box[3] = {16, TC_DCH, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.q, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(q) failed: %d", (int)r);
+  } else {
+    memset(&qmap, 0, sizeof(qmap));
+  }
+  {   // augmentation image as rows of one 8-code group (64 floats, already in the UMMA no-swizzle layout): only the pair
+      // kernel loads it through a tensor map (a tensor load may signal the barrier of the peer CTA)
+    cuuint64_t dims[2] = {64, (cuuint64_t)(g.nb * g.BN / 8)};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? g.BN / 16 : g.BN / 8)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)eaug_img, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(augmentation) failed: %d", (int)r);
+  }
   uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
   uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
   const int ktot = g.nb * g.BN;
@@ -1656,7 +1864,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
   P.stage_bytes = (uint32_t)g.stage_bytes; P.off_stage = (uint32_t)g.off_stage;
   P.off_aug = (uint32_t)g.off_aug; P.off_aaug = (uint32_t)g.off_aaug;
   P.off_pub = (uint32_t)g.off_pub; P.off_zn = (uint32_t)g.off_zn;
-  P.off_ctab = (uint32_t)g.off_ctab; P.off_bar = (uint32_t)g.off_bar;
+  P.off_ctab = (uint32_t)g.off_ctab; P.off_qst = (uint32_t)g.off_qst; P.off_bar = (uint32_t)g.off_bar;
   P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
   P.counts = a.stats ? a.ws.counts : nullptr;
   P.sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
@@ -1666,19 +1874,44 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
   P.dbg = dbg;
 
   int grid = sm_count_tc();
-  if (grid > P.ntiles) grid = P.ntiles;
+  if (pair) {                                  // one 2-CTA cluster per tile pair, at most one CTA per SM
+    const int npairs = (P.ntiles + 1) / 2;
+    int nclusters = grid / 2;
+    if (nclusters > npairs) nclusters = npairs;
+    grid = 2 * nclusters;
+  } else if (grid > P.ntiles) {
+    grid = P.ntiles;
+  }
   const bool stats = a.stats != nullptr;
-  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const TcsParams);
-  KernFn kern = dbg ? (stats ? vq_assign_tcs_kernel<true, true> : vq_assign_tcs_kernel<true, false>)
-                    : (stats ? vq_assign_tcs_kernel<false, true> : vq_assign_tcs_kernel<false, false>);
-  const int ki = (dbg ? 2 : 0) + (stats ? 1 : 0);
-  static bool attr_set[4] = {false, false, false, false};
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcsParams);
+  static const KernFn kerns[8] = {
+      vq_assign_tcs_kernel<false, false, false>, vq_assign_tcs_kernel<false, true, false>,
+      vq_assign_tcs_kernel<true, false, false>,  vq_assign_tcs_kernel<true, true, false>,
+      vq_assign_tcs_kernel<false, false, true>,  vq_assign_tcs_kernel<false, true, true>,
+      vq_assign_tcs_kernel<true, false, true>,   vq_assign_tcs_kernel<true, true, true>};
+  const int ki = (pair ? 4 : 0) + (dbg ? 2 : 0) + (stats ? 1 : 0);
+  KernFn kern = kerns[ki];
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[ki]) {
     VQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_set[ki] = true;
   }
   const bool prof = profile_begin(s);
-  kern<<<grid, TC_THREADS, g.total, s>>>(zmap, emap, P);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = g.total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, zmap, emap, amap, qmap, P));
+  } else {
+    kern<<<grid, TC_THREADS, g.total, s>>>(zmap, emap, amap, qmap, P);
+  }
   if (prof) profile_end(s);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());

@@ -47,6 +47,7 @@ int vq_assign_fwd(const float* z, int B, int D, int H, int W, const float* embed
   a.z = z; a.B = B; a.D = D; a.H = H; a.W = W; a.embed = embed; a.K = K;
   a.ids = ids; a.ids_nat = ids_nat; a.q = q; a.loss = loss; a.stats = stats; a.snapshot = embed_snapshot;
   a.ws = carve_workspace(workspace, N, K, D);
+  a.flags = flags;
   cudaStream_t s = (cudaStream_t)stream;
 
   const bool use_small = stats == nullptr && !(flags & (VQ_FLAG_FORCE_SIMT | VQ_FLAG_FORCE_TC)) &&

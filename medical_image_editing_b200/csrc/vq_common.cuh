@@ -99,6 +99,7 @@ struct FwdArgs {
   const float* embed; int K;
   int64_t* ids; int32_t* ids_nat; float* q; float* loss; float* stats; float* snapshot;
   Workspace ws;
+  int flags = 0;
 };
 
 int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s);

@@ -450,6 +450,78 @@ def test_simt_and_auto_paths_agree_at_full_size():
     assert rel_err(outs[1][4], outs[0][4]) <= TOL
 
 
+# The streamed-codebook kernel can run as 2-CTA clusters (VQ_FLAG_PAIR; cta_group::2: each CTA holds half of every 256-code
+# slice); the default is one CTA per tile.  Both must produce the same bits.
+PAIR_SHAPES = [(16, 256, 512, 256, "clustered"), (4, 128, 512, 128, "gauss"), (2, 64, 4096, 64, "gauss"),
+               (1, 16, 512, 256, "relu"), (3, 48, 1000, 132, "gauss"), (2, 96, 4096, 256, "clustered")]
+
+
+@pytest.mark.parametrize("B,H,K,D,kind", PAIR_SHAPES)
+def test_streamed_pair_and_single_cta_kernels_agree(B, H, K, D, kind):
+    gen = torch.Generator(device=DEV).manual_seed(77 + K + D)
+    embed = torch.randn(K, D, device=DEV, generator=gen)
+    if kind == "clustered":
+        z = embed[torch.randint(0, K, (B, H, H), device=DEV, generator=gen)].permute(0, 3, 1, 2).contiguous()
+        z = z + 0.1 * torch.randn(B, D, H, H, device=DEV, generator=gen)
+    else:
+        z = torch.randn(B, D, H, H, device=DEV, generator=gen)
+        if kind == "relu":
+            z = torch.relu(z)
+    outs = []
+    for flags in (0, _native.VQ_FLAG_PAIR, _native.VQ_FLAG_FORCE_SIMT):
+        m = new_vq(K, D, 0.99, flags)
+        with torch.no_grad():
+            m.embed.copy_(embed)
+            m.cluster_size.fill_(float(B * H * H) / K)
+            m.embed_avg.copy_((embed * m.cluster_size[:, None]).T)
+        m.eval()
+        with torch.no_grad():
+            q2, loss2, ids2 = m(z)                                 # the inference instantiation (no statistics)
+        m.train(True)
+        zz = z.clone().requires_grad_(True)
+        q, loss, ids = m(zz)
+        (gz,) = torch.autograd.grad(q.sum() + loss, zz)
+        outs.append((ids, q.detach(), loss.detach(), m.cluster_size.clone(), m.embed.clone(), gz, ids2, q2, loss2))
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
+        assert abs(outs[0][2].item() - o[2].item()) <= TOL * abs(outs[0][2].item())
+        assert torch.equal(outs[0][3], o[3])
+        assert rel_err(o[4], outs[0][4]) <= TOL and rel_err(o[5], outs[0][5]) <= TOL
+        assert torch.equal(outs[0][6], o[6]) and torch.equal(outs[0][7], o[7])
+        assert abs(outs[0][8].item() - o[8].item()) <= TOL * abs(outs[0][8].item())
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 8, 16), (1, 16, 24), (5, 8, 48)])
+def test_streamed_pair_kernel_odd_tile_count(B, H, W):
+    """An odd number of 128-pixel tiles (only reachable through the C-ABI: the module takes square maps, whose tile
+    count is even): the odd CTA of the last pair gets a tile past the end and must not write anything."""
+    K, D = 512, 128
+    L = pkg.lib()
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    z = torch.randn(B, D, H, W, device=DEV, generator=gen)
+    embed = torch.randn(K, D, device=DEV, generator=gen)
+    assert (B * H * W // 128) % 2 == 1
+    res = []
+    for flags in (_native.VQ_FLAG_FORCE_TC, _native.VQ_FLAG_PAIR | _native.VQ_FLAG_FORCE_TC, _native.VQ_FLAG_FORCE_SIMT):
+        q = torch.full((B, D, H, W), -7.0, device=DEV)
+        guard = torch.full((4096,), -7.0, device=DEV)              # memory right behind q must stay untouched
+        ids = torch.full((B, W, H), -1, dtype=torch.int64, device=DEV)
+        loss = torch.zeros((), device=DEV)
+        stats = torch.zeros(L.vq_stats_floats(K, D), device=DEV)
+        ws = torch.empty(L.vq_workspace_bytes(B * H * W, K, D), dtype=torch.uint8, device=DEV)
+        _native.check(L.vq_assign_fwd(z.data_ptr(), B, D, H, W, embed.data_ptr(), K, ids.data_ptr(), None, q.data_ptr(),
+                                      loss.data_ptr(), stats.data_ptr(), None, ws.data_ptr(), ws.numel(), flags,
+                                      torch.cuda.current_stream().cuda_stream), "vq_assign_fwd")
+        torch.cuda.synchronize()
+        assert bool((guard == -7.0).all())
+        res.append((ids, q, loss, stats))
+    for r in res[1:]:
+        assert torch.equal(res[0][0], r[0]) and torch.equal(res[0][1], r[1])
+        assert abs(res[0][2].item() - r[2].item()) <= TOL * abs(res[0][2].item())
+        assert rel_err(r[3], res[0][3]) <= TOL
+    assert int(res[1][0].min()) >= 0
+
+
 def test_multistep_cold_training_paths_agree():
     """Several training steps from the cold state (cluster_size == 0): dead codes explode, many pixels
     collapse onto a few live codes, candidate lists overflow -- the tensor-core path (with its exhaustive
