@@ -152,6 +152,14 @@ int vq_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels
                       const float* weights, float* g_z, int B, int D, int H, int W, int K, vq_stream_t stream);
 
 /*
+ * One-hot of an integer label map, channel-major (replaces functions/onehot.py:5-20, the
+ * `OneHotEncoder` the stage-1 trainers apply to the code map, single_window_trainer.py:91-99):
+ *   labels  int32 or int64 [B, HW] (label_bytes = 4 or 8);  out float [B, C, HW], every element written:
+ *   out[b, c, p] = (labels[b, p] == c).  A label outside [0, C) yields an all-zero column.
+ */
+int vq_onehot(const void* labels, int label_bytes, int64_t B, int64_t HW, int C, float* out, vq_stream_t stream);
+
+/*
  * Measurement hooks (used by bench.py only; they do not change results).
  *   vq_launch_count     number of kernels this library has launched in this process so far.
  *   vq_profile_enable   when on, vq_assign_fwd brackets its dominant kernel (the nearest-code

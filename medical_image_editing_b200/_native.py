@@ -46,6 +46,7 @@ SIGNATURES = {
     "vq_embed_loss_work_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "vq_embed_loss_fwd": (ctypes.c_int, [c_f32p, c_i32p, c_f32p] + [ctypes.c_int] * 5 +
                           [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "vq_onehot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_f32p, ctypes.c_void_p]),
     "vq_embed_loss_bwd": (ctypes.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 5 +
                           [ctypes.c_void_p]),
     "vq_launch_count": (ctypes.c_int64, []),

@@ -96,6 +96,15 @@ int vq_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t*
   return launch_bwd(g_q, g_loss, z, ids_nat, embed_snapshot, g_z, B, D, H, W, K, (cudaStream_t)stream);
 }
 
+int vq_onehot(const void* labels, int label_bytes, int64_t B, int64_t HW, int C, float* out, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B >= 0 && HW >= 0 && C > 0, VQ_ERR_INVALID_ARG, "vq_onehot: bad shape B=%lld HW=%lld C=%d", (long long)B, (long long)HW, C);
+  VQ_REQUIRE(label_bytes == 4 || label_bytes == 8, VQ_ERR_INVALID_ARG, "vq_onehot: labels must be int32 or int64");
+  if (B * HW == 0) return VQ_OK;
+  VQ_REQUIRE(labels && out, VQ_ERR_INVALID_ARG, "vq_onehot: null pointer");
+  return launch_onehot(labels, label_bytes, B, HW, C, out, (cudaStream_t)stream);
+}
+
 size_t vq_embed_loss_work_bytes(int B, int K) {
   if (B <= 0 || K <= 0) return 0;
   return embed_loss_work_bytes(B, K);

@@ -112,6 +112,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 int tc_debug_ncols(int D, int K);
 int tc_debug_timing(long long* host_out, int n);
 int launch_fallback_rows(const FwdArgs& a, cudaStream_t s);
+int launch_onehot(const void* labels, int label_bytes, int64_t B, int64_t HW, int C, float* out, cudaStream_t s);
 int launch_finish(const FwdArgs& a, bool tc_path, cudaStream_t s);
 int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long long avg_sk, float* embed,
                const float* stats, int K, int D, double momentum, double eps, float count_scale, float sum_scale,

@@ -846,4 +846,46 @@ int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int 
   return VQ_OK;
 }
 
+
+// =============================================================================================
+// one-hot of an integer label map, channel-major: labels [B, HW] -> out [B, C, HW] fp32 (functions/onehot.py:5-20 builds it
+// with eye(C).index_select + permute + contiguous + float: three passes over B*HW*C elements).  Pure write stream:
+// thread = four consecutive pixels, one 16-byte streaming store per class; labels outside [0, C) give an all-zero column.
+// =============================================================================================
+template <typename LabelT>
+__global__ void __launch_bounds__(256)
+vq_onehot_kernel(const LabelT* __restrict__ labels, long long HW, int C, float* __restrict__ out, int cblock) {
+  const long long quads = (HW + 3) >> 2;
+  const long long qd = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qd >= quads) return;
+  const long long b = blockIdx.z, p = qd << 2;
+  const int c0 = blockIdx.y * cblock, c1 = min(C, c0 + cblock);
+  long long l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) l[i] = (p + i < HW) ? (long long)labels[b * HW + p + i] : -1;
+  float* o = out + (b * C + c0) * HW + p;
+  if (p + 3 < HW && ((HW & 3) == 0) && (((uintptr_t)out & 15) == 0)) {
+    for (int c = c0; c < c1; ++c, o += HW)
+      __stcs(reinterpret_cast<float4*>(o), make_float4(l[0] == c ? 1.f : 0.f, l[1] == c ? 1.f : 0.f, l[2] == c ? 1.f : 0.f,
+                                                         l[3] == c ? 1.f : 0.f));
+  } else {
+    for (int c = c0; c < c1; ++c, o += HW)
+      for (int i = 0; i < 4; ++i)
+        if (p + i < HW) o[i] = l[i] == c ? 1.f : 0.f;
+  }
+}
+
+int launch_onehot(const void* labels, int label_bytes, int64_t B, int64_t HW, int C, float* out, cudaStream_t s) {
+  if (B == 0 || HW == 0) return VQ_OK;
+  const long long quads = (HW + 3) / 4;
+  const int cblock = C < 32 ? C : 32;                      // classes per CTA: keeps the label quad in registers for 32 stores
+  dim3 grid((unsigned)((quads + 255) / 256), (unsigned)((C + cblock - 1) / cblock), (unsigned)B);
+  VQ_REQUIRE(grid.y <= 65535 && B <= 65535, VQ_ERR_UNSUPPORTED, "vq_onehot: too many classes / images");
+  if (label_bytes == 8) vq_onehot_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)labels, HW, C, out, cblock);
+  else vq_onehot_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)labels, HW, C, out, cblock);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
 }  // namespace vqb200
