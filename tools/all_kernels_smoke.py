@@ -1,5 +1,5 @@
-"""Small launches of every kernel family for a compute-sanitizer pass on the GPU box:
-   compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+"""Small launches of every kernel family (smoke run on the GPU box; compute-sanitizer is closed on this pool):
+   python tools/sanitize_smoke.py"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
