@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(TC_PREP2_THREADS)
 vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, int K, int D, int BN, int nb,
                    float* __restrict__ es, float* __restrict__ eaug_img, int* __restrict__ perm,
                    uint32_t* __restrict__ rmax, uint32_t* __restrict__ meta) {
-  extern __shared__ uint32_t keys[];          // [K] norm bits (NaN / negative -> +inf)
+  extern __shared__ __align__(16) uint32_t keys[];          // [K] norm bits (NaN / negative -> +inf)
   __shared__ int hist[256];
   __shared__ float s_rcap;
   const int tid = threadIdx.x;
@@ -398,7 +398,16 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
     if (real) {
       const uint32_t mine = keys[i];
       int rank = 0;
-      for (int j = 0; j < K; ++j) {           // broadcast reads
+      int j = 0;
+      const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+      for (; j + 4 <= K; j += 4) {            // broadcast reads, four keys per 16-byte load
+        const uint4 kk = k4[j >> 2];
+        rank += (kk.x < mine || (kk.x == mine && j < i)) ? 1 : 0;
+        rank += (kk.y < mine || (kk.y == mine && j + 1 < i)) ? 1 : 0;
+        rank += (kk.z < mine || (kk.z == mine && j + 2 < i)) ? 1 : 0;
+        rank += (kk.w < mine || (kk.w == mine && j + 3 < i)) ? 1 : 0;
+      }
+      for (; j < K; ++j) {
         const uint32_t kj = keys[j];
         rank += (kj < mine || (kj == mine && j < i)) ? 1 : 0;
       }
@@ -427,7 +436,15 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
     const int dq = D >> 2;
     float4* dst = reinterpret_cast<float4*>(es + (size_t)pos * D);
     const float4* src = reinterpret_cast<const float4*>(E + (size_t)(real ? i : 0) * D);
-    for (int j = 0; j < dq; ++j) dst[j] = real ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 8 <= dq; j += 8) {                 // eight 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = real ? __ldg(src + j + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[j + u] = v[u];
+    }
+    for (; j < dq; ++j) dst[j] = real ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

@@ -97,7 +97,21 @@ __global__ void vq_prep_kernel(const float* __restrict__ E, int K, int D, int Kp
     float acc = 0.f;
     if (k < (size_t)K) {
       const float* row = E + k * D;
-      for (int d = 0; d < D; ++d) acc = __fmaf_rn(row[d], row[d], acc);
+      int d = 0;
+      if ((D & 3) == 0 && (((uintptr_t)E) & 15) == 0) {      // four 16-byte loads in flight, then their fmas in ascending d
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        for (; d + 16 <= D; d += 16) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __ldg(r4 + (d >> 2) + u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc = __fmaf_rn(v[u].x, v[u].x, acc); acc = __fmaf_rn(v[u].y, v[u].y, acc);
+            acc = __fmaf_rn(v[u].z, v[u].z, acc); acc = __fmaf_rn(v[u].w, v[u].w, acc);
+          }
+        }
+      }
+      for (; d < D; ++d) acc = __fmaf_rn(row[d], row[d], acc);
     } else {
       acc = INFINITY;  // padding codes can never win: score = 2*0 - inf
     }
@@ -366,7 +380,31 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
       const bool two = k0 + FB_THREADS < Kpad;
       float acc0 = 0.f, acc1 = 0.f, acc0B = 0.f, acc1B = 0.f;   // dot = A + B (even / odd channel quads, vq_common.cuh)
       const float* ep = et + k0 + tid;
-      for (int d8 = 0; d8 < D; d8 += 8) {
+      // Full groups of 16 channels: all 32 loads first (unguarded, so the compiler keeps them in flight together), then
+      // the fmas in the library's chain order.  With the loads guarded one by one (the first version) every load was a
+      // separate L2 round trip: 36 us per call for one or two rows at D = 64, 8 % of the training step.
+      int d8 = 0;
+      for (; d8 + 16 <= D; d8 += 16) {
+        float ea[16], eb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float* row = ep + (size_t)(d8 + u) * Kpad;
+          ea[u] = __ldg(row);
+          eb[u] = two ? __ldg(row + FB_THREADS) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float zv = zr[d8 + u];
+          if ((u & 7) < 4) {
+            acc0 = __fmaf_rn(zv, ea[u], acc0);
+            if (two) acc1 = __fmaf_rn(zv, eb[u], acc1);
+          } else {
+            acc0B = __fmaf_rn(zv, ea[u], acc0B);
+            if (two) acc1B = __fmaf_rn(zv, eb[u], acc1B);
+          }
+        }
+      }
+      for (; d8 < D; d8 += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int d = d8 + u;
@@ -449,7 +487,15 @@ __global__ void vq_finish_kernel(const double* __restrict__ loss_acc, float* __r
       const int kd = K * D;
       for (int i = tid; i < kd; i += gridDim.x * blockDim.x) {
         float acc = stats[sums_off + i];
-        for (int r = 0; r < nrep - 1; ++r) acc += sums_rep[(size_t)r * kd + i];
+        int r = 0;
+        for (; r + 8 <= nrep - 1; r += 8) {                   // eight replica loads in flight, added in the fixed order
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(sums_rep + (size_t)(r + u) * kd + i);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; r < nrep - 1; ++r) acc += sums_rep[(size_t)r * kd + i];
         stats[sums_off + i] = acc;
       }
     }
