@@ -11,7 +11,8 @@ N > 1] + straight-through/commitment backward) on the quantiser input of BASELIN
 (VQ-W-Net training step, batch 16 of 256x256 slices -> z = 16x64x256x256, K = 512): 1,048,576
 lookups per GPU per step (weak scaling: 16 slices per GPU).
 
-One JSON line on stdout (rank 0).  `value` = whole-job lookups/s with inputs resident in HBM;
+One JSON line on stdout (rank 0).  `value` = whole-job lookups/s with inputs resident in HBM (the timed region replays
+CUDA graphs of the step; `eager` = the same loop launched from Python, `--no-graphs` makes that the timed region);
 `e2e` = the same through the module's public API with HOST (pinned) input and the result (loss +
 code map) read back every step; `roofline` = the dominant kernel (nearest-code search) against the
 measured HBM peak; `cpu_baseline` = the oracle (a port of the reference's torch op chain) on the
@@ -264,28 +265,36 @@ def run_b200_arm(args, wl, wl_name):
         step(i)
     barrier()
 
-    # N > 1: a step is ~0.5 ms of GPU work behind ~25 host-side enqueues (allocations, three C-ABI calls, the NCCL
-    # launch, stream fork/join), and eight ranks share one box's host cores: the eager loop is launch-bound there (0.51 to
-    # 0.59 ms per step from run to run).  Capture one CUDA graph per input buffer (forward + overlapped statistics
-    # exchange + backward, the exchange joined inside the step) and replay them in the timed region.  The search
-    # kernel's own time (roofline) cannot be bracketed with events inside a graph: it is measured over the same number
-    # of eager steps right before the timed region.
-    use_graphs = world > 1 and not args.no_graphs
+    # A step is ~0.4 ms of GPU work behind ~25 host-side enqueues (allocations, three C-ABI calls, for N > 1 the NCCL
+    # launch and a stream fork/join), and the ranks of one box share its host cores: the eager loop is launch-bound
+    # (N = 1: 0.43 ms eager against 0.40 ms replayed; N = 8: 0.51 to 0.59 ms eager from run to run).  The timed region
+    # therefore replays CUDA graphs -- one per input buffer: forward + overlapped statistics exchange + backward, the
+    # exchange joined inside the step (`--no-graphs`: eager loop).  Events cannot bracket a kernel inside a graph, so
+    # the search kernel's own time (roofline) is measured with the library's events over the same number of EAGER steps
+    # right before; that eager loop is itself timed and reported as `eager`.
+    use_graphs = not args.no_graphs
+    sampler = ClockSampler(local) if rank == 0 else None
     tot_ms, nl = ctypes.c_double(0), ctypes.c_int(0)
-    graphs = []
+    L.vq_profile_enable(1)
+    L.vq_profile_read(None, None)
+    launches0 = L.vq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = L.vq_launch_count() - launches0               # per-step launches are the same when the graphs replay them
+    L.vq_profile_read(ctypes.byref(tot_ms), ctypes.byref(nl))
+    L.vq_profile_enable(0)
+    eager_ms = e0.elapsed_time(e1)
+    elapsed_ms = eager_ms
     if use_graphs:
-        L.vq_profile_enable(1)
-        L.vq_profile_read(None, None)
-        l0 = L.vq_launch_count()
-        for i in range(args.steps):
-            step(i)
-        barrier()
-        launches_per_step = (L.vq_launch_count() - l0) / args.steps
-        L.vq_profile_read(ctypes.byref(tot_ms), ctypes.byref(nl))
-        L.vq_profile_enable(0)
         vq.sync_codebook()
         pool = torch.cuda.graph_pool_handle()
         cap = torch.cuda.Stream(device=dev)
+        graphs = []
         for bidx in range(NBUF):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool, stream=cap):
@@ -295,35 +304,17 @@ def run_b200_arm(args, wl, wl_name):
         for bidx in range(NBUF):                               # one untimed replay of every graph
             graphs[bidx][0].replay()
         barrier()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if not use_graphs:
-        L.vq_profile_enable(1)
-        L.vq_profile_read(None, None)
-    launches0 = L.vq_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record()
-    if use_graphs:
+        e0.record()
         for i in range(args.steps):
             graphs[i % NBUF][0].replay()
-    else:
-        for i in range(args.steps):
-            step(i)
-    e1.record()
-    barrier()
+        e1.record()
+        barrier()
+        elapsed_ms = e0.elapsed_time(e1)
     t_wall1 = time.time()
-    elapsed_ms = e0.elapsed_time(e1)
-    if use_graphs:
-        launches = int(round(launches_per_step * args.steps))  # kernels replayed: counted on the eager steps of the same loop
-    else:
-        launches = L.vq_launch_count() - launches0
-        L.vq_profile_read(ctypes.byref(tot_ms), ctypes.byref(nl))
-        L.vq_profile_enable(0)
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([elapsed_ms, eager_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms, eager_ms = float(t[0].item()), float(t[1].item())
 
     # ---- e2e: host (pinned) input -> module -> loss + code map back on the host, every step --------------
     # The way a training loop feeds the module: a copy stream prefetches step i+1's batch (pinned host -> HBM, double
@@ -452,7 +443,8 @@ def run_b200_arm(args, wl, wl_name):
                                                           "ema_state": "cold" if args.cold else "warmed",
                                                           "stats_exchange": ("none" if world == 1 else "inline" if args.inline_exchange
                                                                              else "packed all-reduce + EMA on a side stream"),
-                                                          "launch": ("CUDA graphs (one per input buffer, whole step incl. NCCL), kernel_ms from eager steps"
+                                                          "launch": ("CUDA-graph replay (one graph per input buffer: whole step incl. the NCCL exchange); "
+                                                                     "roofline kernel_ms from the eager loop timed right before (`eager`)"
                                                                      if use_graphs else "eager")}),
             "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": z_host[0].numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
@@ -464,6 +456,7 @@ def run_b200_arm(args, wl, wl_name):
             "cpu_baseline": cpu,
             "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms,
                              "fallback_rows": fb_rows},
+            "eager": {"value": world * n_per_gpu * args.steps / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms / args.steps},
             "vqwnet_train": wnet,
         }
         print(json.dumps(out), flush=True)
@@ -689,7 +682,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
     ap.add_argument("--inline-exchange", action="store_true", help="N > 1: all-reduce + EMA update on the compute stream")
-    ap.add_argument("--no-graphs", action="store_true", help="N > 1: eager step loop instead of CUDA-graph replay")
+    ap.add_argument("--no-graphs", action="store_true", help="eager step loop in the timed region instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "vqwnet":
