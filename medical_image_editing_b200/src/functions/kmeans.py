@@ -49,7 +49,7 @@ def _lloyd(z_dn: torch.Tensor, centers: torch.Tensor, tol: float, iter_limit: in
             if is_distributed():
                 import torch.distributed as dist
                 dist.all_reduce(stats)
-            counts = stats[:K] + stats[K:2 * K]                         # the histogram travels as two exact fp32 halves
+            counts = stats[:K] * 4096.0 + stats[K:2 * K]                # the histogram travels as two exact fp32 halves (c >> 12, c & 4095)
             sums = stats[soff:soff + K * D].view(K, D)
             new = sums / counts[:, None]                                # 0 / 0 = NaN for an empty cluster, as the package
             if empty == "keep":

@@ -85,7 +85,7 @@ def test_onehot_cuda_large_and_edge_cases():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,d,k", [(8192, 16, 10), (4096, 64, 32), (5000, 12, 7)])
+@pytest.mark.parametrize("n,d,k", [(8192, 16, 10), (4096, 64, 32), (5000, 12, 7), (65536, 8, 4)])   # last: > 4096 points per cluster
 def test_kmeans_cuda_matches_oracle(n, d, k):
     """Same initial centres -> same Lloyd iterations: centres within 1e-4, assignments equal.  n = 5000 takes the fp32
     CUDA-core search (N % 128 != 0)."""
@@ -124,3 +124,37 @@ def test_kmeans_initialize_embed_single_process():
         sel = flat[ids.reshape(-1) == kk]
         if len(sel):
             assert (sel.mean(0) - vq.embed[kk]).abs().max() < 2e-2              # fixed point up to the stopping tolerance
+
+
+def _kmeans_dp_worker(rank, ws, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(ws), RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    from medical_image_editing_b200.src.functions import kmeans_nchw
+    B, D, H, K = 4, 16, 64, 10
+    X, _ = _blobs(B * H * H, D, K, seed=21)
+    embed = X.view(B, H, H, D).permute(0, 3, 1, 2).contiguous()
+    half = B // ws
+    c, it = kmeans_nchw(embed[rank * half:(rank + 1) * half].to(f"cuda:{rank}"), K, seed=5)
+    ret[rank] = (c.cpu().numpy(), it)
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_kmeans_two_ranks_match_single_process():
+    """Data-parallel Lloyd: each rank assigns its shard, the packed statistics are all-reduced; both ranks end with
+    bit-identical centres, equal (up to the stopping tolerance) to one process on the whole batch."""
+    import torch.multiprocessing as mp
+    from medical_image_editing_b200.src.functions import kmeans_nchw
+    ret = mp.Manager().dict()
+    mp.spawn(_kmeans_dp_worker, args=(2, 29791, ret), nprocs=2, join=True)
+    os.environ.pop("WORLD_SIZE", None)
+    os.environ.pop("RANK", None)
+    assert np.array_equal(ret[0][0], ret[1][0]) and ret[0][1] == ret[1][1]
+    B, D, H, K = 4, 16, 64, 10
+    X, _ = _blobs(B * H * H, D, K, seed=21)
+    embed = X.view(B, H, H, D).permute(0, 3, 1, 2).contiguous().to(DEV)
+    c1, _ = kmeans_nchw(embed, K, seed=5)
+    assert np.abs(ret[0][0] - c1.cpu().numpy()).max() < 5e-2
