@@ -27,7 +27,7 @@ except ImportError:  # dropped into the reference tree
     from utils import get_world_size, is_distributed
 
 
-def _lloyd(z_dn: torch.Tensor, centers: torch.Tensor, tol: float, iter_limit: int, empty: str, want_ids: bool):
+def _lloyd(z_dn: torch.Tensor, centers: torch.Tensor, tol: float, iter_limit: int, empty: str):
     """z_dn: [D, N] fp32 CUDA (channel-major, the layout the search kernels read); centres [K, D].  In-place on `centers`."""
     L = lib()
     D, N = z_dn.shape
@@ -85,7 +85,7 @@ def kmeans(X: torch.Tensor, num_clusters: int, distance: str = "euclidean", tol:
         centers = X[idx].clone()
     else:
         centers = cluster_centers.to(X.device).float().clone()
-    ids, centers, _ = _lloyd(X.t().contiguous(), centers.contiguous(), tol, iter_limit, empty, True)
+    ids, centers, _ = _lloyd(X.t().contiguous(), centers.contiguous(), tol, iter_limit, empty)
     return ids.cpu(), centers.cpu()
 
 
@@ -114,7 +114,7 @@ def kmeans_nchw(embed: torch.Tensor, num_clusters: int, tol: float = 1e-4, iter_
         centers[ks] = z[:, cols].t()
     if ws > 1:
         dist.all_reduce(centers)
-    _, centers, it = _lloyd(z, centers, tol, iter_limit, empty, False)
+    _, centers, it = _lloyd(z, centers, tol, iter_limit, empty)
     return centers, it
 
 
