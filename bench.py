@@ -290,17 +290,32 @@ def run_b200_arm(args, wl, wl_name):
     L.vq_profile_enable(0)
     eager_ms = e0.elapsed_time(e1)
     elapsed_ms = eager_ms
+    graph_note = None
     if use_graphs:
         vq.sync_codebook()
-        pool = torch.cuda.graph_pool_handle()
-        cap = torch.cuda.Stream(device=dev)
         graphs = []
-        for bidx in range(NBUF):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=cap):
-                out_b = step(bidx)
-                vq.sync_codebook()                             # join the side stream inside the captured step
-            graphs.append((g, out_b))
+        try:
+            pool = torch.cuda.graph_pool_handle()
+            cap = torch.cuda.Stream(device=dev)
+            for bidx in range(NBUF):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=cap):
+                    out_b = step(bidx)
+                    vq.sync_codebook()                         # join the side stream inside the captured step
+                graphs.append((g, out_b))
+            ok = 1.0
+        except Exception as exc:                               # keep the line: fall back to the eager loop's time
+            graph_note = f"graph capture failed ({type(exc).__name__}: {exc})"[:200]
+            ok = 0.0
+        okt = torch.tensor([ok], device=dev)
+        if world > 1:                                          # capture is rank-local (NCCL only talks at replay): agree first
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        use_graphs = bool(okt.item() > 0.5)
+        if not use_graphs:
+            graphs = []
+            graph_note = graph_note or "graph capture failed on another rank"
+            torch.cuda.synchronize()
+    if use_graphs:
         for bidx in range(NBUF):                               # one untimed replay of every graph
             graphs[bidx][0].replay()
         barrier()
@@ -445,7 +460,7 @@ def run_b200_arm(args, wl, wl_name):
                                                                              else "packed all-reduce + EMA on a side stream"),
                                                           "launch": ("CUDA-graph replay (one graph per input buffer: whole step incl. the NCCL exchange); "
                                                                      "roofline kernel_ms from the eager loop timed right before (`eager`)"
-                                                                     if use_graphs else "eager")}),
+                                                                     if use_graphs else (graph_note or "eager loop (--no-graphs)"))}),
             "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": z_host[0].numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
                     "overlap": "step i+1 H2D (copy stream, double buffer) overlaps step i kernels; result read every step",
@@ -461,7 +476,7 @@ def run_b200_arm(args, wl, wl_name):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
-        if use_graphs:
+        if not args.no_graphs:                                  # also when the capture was attempted and abandoned
             # NCCL kernels captured into CUDA graphs: tearing the process group down with the graphs around hung on the
             # GPU box (after the line had been printed).  Make sure every rank is done, then leave without the teardown.
             barrier()
