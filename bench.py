@@ -231,7 +231,7 @@ def run_b200_arm(args, wl, wl_name):
     g_q = torch.randn(B, D, H, H, device=dev, generator=gen)
     one = torch.ones((), device=dev)
     # N > 1: the all-reduce of the EMA statistics and the EMA update run on a side stream, behind the backward
-    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch",
+    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch", reduce_mode="sum",
                 overlap_exchange=(world > 1 and not args.inline_exchange)).to(dev)
     if args.simt:
         vq.kernel_flags = 1
@@ -523,7 +523,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     B, H = WNET["B"], WNET["H"]
     torch.manual_seed(0)
     model = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch",
-                                            overlap_exchange=(world > 1 and not inline_exchange)),
+                                            reduce_mode="sum", overlap_exchange=(world > 1 and not inline_exchange)),
                         1, dict_size=WNET["K"]).to(dev)
     trainer = DataParallelVQTrainer(model, lr=WNET["lr"], commit_weight=WNET["commit_weight"])
     host = wnet_images(4, B, H, 4321 + rank, pin=True)

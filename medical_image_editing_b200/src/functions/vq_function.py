@@ -39,10 +39,18 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
 
 def wait_pending_update(embed: torch.Tensor) -> None:
     """Make the current stream wait for an overlapped EMA update of this codebook (no-op when none is in flight).
-    Called before anything reads or writes the buffers: the next forward, `lookup`, `get_codebook`, `state_dict`."""
-    ev = _PENDING.pop(embed.data_ptr(), None) if embed.is_cuda else None
+    Called before anything reads or writes the buffers: the next forward, `lookup`, `get_codebook`, `state_dict`,
+    `load_state_dict`, `.to()` / `.cuda()` and buffer reassignment (vq_module.py hooks).  The event stays registered
+    until it has completed (or the next forward replaces it), so EVERY stream that touches the buffers waits, not
+    only the first caller's."""
+    if not embed.is_cuda:
+        return
+    key = embed.data_ptr()
+    ev = _PENDING.get(key)
     if ev is not None:
         torch.cuda.current_stream(embed.device).wait_event(ev)
+        if ev.query():                  # finished: later readers on any stream need no dependency
+            _PENDING.pop(key, None)
 
 
 
@@ -89,9 +97,79 @@ def _all_reduce_stats(stats: torch.Tensor, K: int, reduce_mode: str) -> Tuple[fl
     raise ValueError(f"reduce_mode must be one of {REDUCE_MODES}, got {reduce_mode!r}")
 
 
+class StatsAccumulator:
+    """EMA statistics of several forward calls (micro-batches) summed before ONE exchange + ONE EMA update, so that
+    n micro-batches equal one forward on their concatenation ("Memory at 2 GPUs in config 5"):
+    every micro-batch is assigned with the same, not yet updated codebook, the packed `[cnt_hi | cnt_lo | sums]`
+    buffers add up exactly (counts) / in fp32 (sums), and `vq_ema_update` runs once, after the last one."""
+
+    def __init__(self, steps: int) -> None:
+        if steps < 1:
+            raise ValueError("accumulate_steps must be >= 1")
+        self.steps = int(steps)
+        self.buf: Optional[torch.Tensor] = None
+        self.count = 0
+
+    def add(self, stats: torch.Tensor) -> bool:
+        """Adds one call's statistics; True when the update is due."""
+        if self.count == 0 or self.buf is None or self.buf.shape != stats.shape or self.buf.device != stats.device:
+            self.buf = stats.clone()
+            self.count = 1
+        else:
+            self.buf.add_(stats)
+            self.count += 1
+        return self.count >= self.steps
+
+    def take(self) -> Optional[torch.Tensor]:
+        buf, self.buf, self.count = (self.buf if self.count else None), None, 0
+        return buf
+
+
+def _exchange_and_update(embed, cluster_size, embed_avg, stats, momentum, eps, reduce_mode, overlap_exchange, scratch_main):
+    """[all-reduce of the packed statistics] + `vq_ema_update` on the current stream, or -- `overlap_exchange` with
+    WORLD_SIZE > 1 -- on the side stream behind whatever the caller enqueues next (vq_module.py:187-199)."""
+    L = lib()
+    dev = embed.device
+    K, D = embed.shape
+    if not (cluster_size.is_contiguous() and embed.is_contiguous()):
+        raise RuntimeError("B200 VQ: the embed / cluster_size buffers must be contiguous")
+    if tuple(embed_avg.shape) != (D, K) or tuple(cluster_size.shape) != (K,):
+        raise RuntimeError("B200 VQ: embed_avg must be [emb_dim, dict_size] and cluster_size [dict_size]")
+    # embed_avg = embed.T.clone() keeps strides (1, D) (vq_module.py:156): pass them through
+    sd, sk = embed_avg.stride()
+
+    def run(scratch, stream_handle):
+        cscale, sscale = 1.0, 1.0
+        if is_distributed():
+            cscale, sscale = _all_reduce_stats(stats, K, reduce_mode)
+        check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), sd, sk, embed.data_ptr(),
+                              stats.data_ptr(), K, D, float(momentum), float(eps), cscale, sscale,
+                              scratch.data_ptr(), stream_handle), "vq_ema_update")
+
+    if overlap_exchange and is_distributed():
+        # The updated codebook is not needed before the next forward (q was gathered from the old one, the backward
+        # uses the snapshot): run the all-reduce and the EMA update on a side stream so they overlap whatever the
+        # caller enqueues next (the backward, the decoder); `wait_pending_update` joins the streams before the buffers
+        # are touched again.
+        cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        scratch = torch.empty(64, dtype=torch.uint8, device=dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            run(scratch, side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(side)
+        for t_ in (stats, scratch):
+            t_.record_stream(side)
+        _PENDING[embed.data_ptr()] = done
+    else:
+        run(scratch_main, _stream())
+
+
 class VQFunction(torch.autograd.Function):
-    """`VQFunction.apply(z, embed, cluster_size, embed_avg, momentum, eps, training, reduce_mode, flags)
-    -> (quantized, commit_loss, ids)`.
+    """`VQFunction.apply(z, embed, cluster_size, embed_avg, momentum, eps, training, reduce_mode, flags,
+    overlap_exchange, accumulator) -> (quantized, commit_loss, ids)`.
 
     * `quantized` [B,D,H,W] (contiguous NCHW), gathered from the codebook as it was BEFORE this
       call's EMA update (vq_module.py:179 precedes :199); gradient passes straight through to `z`.
@@ -104,7 +182,7 @@ class VQFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, embed, cluster_size, embed_avg, momentum, eps, training,
-                reduce_mode="sum", flags=0, overlap_exchange=False):
+                reduce_mode="reference", flags=0, overlap_exchange=False, accumulator=None):
         _require_cuda(z, "input")
         _require_cuda(embed, "embed")
         if z.dim() != 4:
@@ -137,41 +215,14 @@ class VQFunction(torch.autograd.Function):
                                   q.data_ptr(), loss.data_ptr(), _ptr(stats), _ptr(snap),
                                   ws.data_ptr(), ws.numel(), int(flags), _stream()), "vq_assign_fwd")
             if training:
-                if not (cluster_size.is_contiguous() and embed.is_contiguous()):
-                    raise RuntimeError("B200 VQ: the embed / cluster_size buffers must be contiguous")
-                if tuple(embed_avg.shape) != (D, K) or tuple(cluster_size.shape) != (K,):
-                    raise RuntimeError("B200 VQ: embed_avg must be [emb_dim, dict_size] and cluster_size [dict_size]")
-                # embed_avg = embed.T.clone() keeps strides (1, D) (vq_module.py:156): pass them through
-                sd, sk = embed_avg.stride()
-
-                def exchange_and_update(stream_handle):
-                    cscale, sscale = 1.0, 1.0
-                    if is_distributed():
-                        cscale, sscale = _all_reduce_stats(stats, K, reduce_mode)
-                    check(L.vq_ema_update(cluster_size.data_ptr(), embed_avg.data_ptr(), sd, sk, embed.data_ptr(),
-                                          stats.data_ptr(), K, D, float(momentum), float(eps), cscale, sscale,
-                                          scratch.data_ptr(), stream_handle), "vq_ema_update")
-
-                if overlap_exchange and is_distributed():
-                    # The updated codebook is not needed before the next forward (q was gathered from the old one,
-                    # the backward uses the snapshot): run the all-reduce and the EMA update on a side stream so they
-                    # overlap whatever the caller enqueues next (the backward, the decoder); `wait_pending_update`
-                    # joins the streams before the buffers are touched again.
-                    cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
-                    scratch = torch.empty(64, dtype=torch.uint8, device=dev)
-                    ready = torch.cuda.Event()
-                    ready.record(cur)
-                    side.wait_event(ready)
-                    with torch.cuda.stream(side):
-                        exchange_and_update(side.cuda_stream)
-                        done = torch.cuda.Event()
-                        done.record(side)
-                    for t_ in (stats, scratch):
-                        t_.record_stream(side)
-                    _PENDING[embed.data_ptr()] = done
-                else:
-                    scratch = ws
-                    exchange_and_update(_stream())
+                due = True
+                if accumulator is not None and accumulator.steps > 1:
+                    due = accumulator.add(stats)          # micro-batch: the update waits for the last one
+                    if due:
+                        stats = accumulator.take()
+                if due:
+                    _exchange_and_update(embed, cluster_size, embed_avg, stats, momentum, eps, reduce_mode,
+                                         overlap_exchange, ws)
         if need_bwd:
             ctx.save_for_backward(zc, ids_nat, snap)
         ctx.shape = (B, D, H, W, K)
@@ -191,7 +242,7 @@ class VQFunction(torch.autograd.Function):
             g_z = torch.empty_like(zc)
             check(lib().vq_bwd(_ptr(g_q), _ptr(g_loss), zc.data_ptr(), ids_nat.data_ptr(), snap.data_ptr(),
                                g_z.data_ptr(), B, D, H, W, K, _stream()), "vq_bwd")
-        return g_z, None, None, None, None, None, None, None, None, None
+        return g_z, None, None, None, None, None, None, None, None, None, None
 
 
 def vq_lookup(ids: torch.Tensor, embed: torch.Tensor, nchw_friendly: bool = True) -> torch.Tensor:

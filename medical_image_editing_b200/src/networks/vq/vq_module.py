@@ -13,22 +13,27 @@ import torch
 from torch import nn
 
 try:  # package layout
-    from ...functions.vq_function import VQFunction, vq_lookup, wait_pending_update, REDUCE_MODES
+    from ...functions.vq_function import (VQFunction, vq_lookup, wait_pending_update, REDUCE_MODES, StatsAccumulator,
+                                          _exchange_and_update)
 except ImportError:  # dropped into the reference tree: src/functions/vq_function.py
-    from functions.vq_function import VQFunction, vq_lookup, wait_pending_update, REDUCE_MODES
+    from functions.vq_function import (VQFunction, vq_lookup, wait_pending_update, REDUCE_MODES, StatsAccumulator,
+                                       _exchange_and_update)
 
 
 class VQModule(nn.Module):
     """`VQ(emb_dim, dict_size, momentum, eps, knn_backend)` (reference :139-157).
 
     Extra, optional keyword (not in the reference): `reduce_mode` selects what WORLD_SIZE > 1 means
-    for the EMA statistics: "sum" (default; identical to one process on the concatenated batch),
-    "mean" (counts and sums averaged), "reference" (the reference as written, :188-192: rank-local
-    counts, averaged sums).  `knn_backend` is accepted and ignored, as the reference does when faiss
+    for the EMA statistics: "reference" (default: the reference as written, :188-192 -- rank-local counts,
+    sums averaged over the ranks; a drop-in user gets the reference's buffers), "sum" (identical to one process
+    on the concatenated batch; what this package's own data-parallel trainer and bench ask for: replicas stay
+    bit-identical without buffer broadcasts), "mean" (counts and sums averaged).  `knn_backend` is accepted and ignored, as the reference does when faiss
     is absent (:120).  `overlap_exchange=True` runs the all-reduce of the statistics and the EMA update on a side
     stream (they are not needed before the next forward), hidden behind the backward / decoder work the caller
     enqueues next; every access through this module (`forward`, `lookup`, `get_codebook`, `state_dict`) joins the
-    streams first.  Read the buffer attributes directly only after `sync_codebook()`."""
+    streams first.  Read the buffer attributes directly only after `sync_codebook()`.  `accumulate_steps=n` sums the
+    EMA statistics of n training forwards (micro-batches) and applies them in one exchange + one update after the n-th
+    (== one forward on the concatenated batch); `flush_ema()` applies a partial accumulation."""
 
     def __init__(self,
                  emb_dim: int,
@@ -36,8 +41,9 @@ class VQModule(nn.Module):
                  momentum: float,
                  eps: float,
                  knn_backend: Optional[str] = "torch",
-                 reduce_mode: str = "sum",
+                 reduce_mode: str = "reference",
                  overlap_exchange: bool = False,
+                 accumulate_steps: int = 1,
                  ) -> None:
         super().__init__()
         if reduce_mode not in REDUCE_MODES:
@@ -50,21 +56,65 @@ class VQModule(nn.Module):
         self.reduce_mode = reduce_mode
         self.overlap_exchange = overlap_exchange
         self.kernel_flags = 0
+        # micro-batching (BASELINE config 5 at 2 / 4 GPUs): the EMA statistics of `accumulate_steps` training forwards
+        # are summed and applied in ONE exchange + update after the last one == one forward on the concatenated batch
+        self._accumulator = StatsAccumulator(accumulate_steps)
 
         embed = torch.randn(self.dict_size, self.emb_dim)
         self.register_buffer('embed', embed)
         self.register_buffer('cluster_size', torch.zeros(self.dict_size))
         self.register_buffer('embed_avg', self.embed.T.clone())
         self._register_state_dict_hook(lambda module, *a: module.sync_codebook())      # checkpoints see the update
+        # a checkpoint load copies into the buffers in place: an update still in flight on the side stream must land first
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.sync_codebook())
+
+    _BUFFERS = ("embed", "cluster_size", "embed_avg")
 
     def sync_codebook(self) -> None:
         """Join an overlapped EMA update (no-op otherwise) before the buffers are read outside this module."""
-        wait_pending_update(self.embed)
+        embed = self._buffers.get("embed") if "_buffers" in self.__dict__ else None
+        if embed is not None:
+            wait_pending_update(embed)
+
+    def __setattr__(self, name, value):
+        # `self.vq.embed = centres` (unet_encoder.py:85): the old tensor may still be written by the side stream; the
+        # current stream waits for that update before the tensor is dropped (and its memory possibly reused)
+        if name in self._BUFFERS and "_buffers" in self.__dict__ and name in self._buffers:
+            self.sync_codebook()
+        super().__setattr__(name, value)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace the buffers: join the side stream first
+        self.sync_codebook()
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         return VQFunction.apply(input, self.embed, self.cluster_size, self.embed_avg,
                                 self.momentum, self.eps, self.training, self.reduce_mode, self.kernel_flags,
-                                self.overlap_exchange)
+                                self.overlap_exchange, self._accumulator)
+
+    @property
+    def accumulate_steps(self) -> int:
+        return self._accumulator.steps
+
+    @accumulate_steps.setter
+    def accumulate_steps(self, n: int) -> None:
+        self.flush_ema()
+        self._accumulator = StatsAccumulator(n)
+
+    @torch.no_grad()
+    def flush_ema(self) -> bool:
+        """Apply the statistics accumulated so far (fewer than `accumulate_steps` micro-batches) now.  Returns True
+        when an update was made."""
+        stats = self._accumulator.take()
+        if stats is None:
+            return False
+        self.sync_codebook()
+        with torch.cuda.device(self.embed.device):
+            scratch = torch.empty(64, dtype=torch.uint8, device=self.embed.device)
+            _exchange_and_update(self.embed, self.cluster_size, self.embed_avg, stats, self.momentum, self.eps,
+                                 self.reduce_mode, self.overlap_exchange, scratch)
+        return True
 
     @torch.no_grad()
     def _quantize(self, input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

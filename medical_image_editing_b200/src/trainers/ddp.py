@@ -6,8 +6,10 @@ same step with `torch.distributed` only:
 
   * once:   parameters AND buffers are broadcast from rank 0 (DDP does the same at construction);
   * step:   forward on this rank's shard of the batch -> `loss = mse(recon, x) + w * commit_loss` (the subset of
-            `_train_first_step` whose dependencies are on the path) -> backward -> ONE flat all-reduce of all
-            gradients (averaged over ranks, as DDP does) -> optimiser step.
+            `_train_first_step` whose dependencies are on the path) -> backward, during which the gradients are
+            all-reduced bucket by bucket (`GradientBuckets`: the `.grad` tensors are views of a few flat buffers,
+            a bucket's all-reduce is launched as soon as its last gradient has been accumulated, so the exchange
+            overlaps the rest of the backward and nothing is concatenated or copied back) -> optimiser step.
   * the quantiser's EMA statistics are all-reduced inside `VQ.forward` (one packed buffer, see
     `functions/vq_function.py`); every rank applies the identical update, so the codebooks stay bit-identical and no
     per-step buffer broadcast is needed (`broadcast_buffers=False` in DDP terms).
@@ -61,6 +63,88 @@ def all_reduce_gradients(params: Iterable[torch.nn.Parameter], group=None, avera
     return off
 
 
+class GradientBuckets:
+    """Gradients as views of flat buckets, all-reduced (averaged) while the backward is still running.
+
+    Parameters are taken in reverse registration order (roughly the order in which autograd finishes them) and packed
+    into buckets of about `bucket_bytes`; every `p.grad` is a view into its bucket, so autograd accumulates in place
+    and a bucket is ready for `all_reduce` the moment its last gradient has landed (post-accumulate hooks).
+    `finish()` waits for the outstanding collectives.  With world size 1 nothing is registered."""
+
+    def __init__(self, params, group=None, bucket_bytes: int = 32 << 20) -> None:
+        self.group = group
+        self.ws = _world(group)
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, self._pending, self._works, self._handles = [], [], [], []
+        self._of = {}
+        if self.ws == 1 or not self.params:
+            return
+        cur, cur_bytes = [], 0
+        groups = []
+        for p in reversed(self.params):
+            if cur and (cur_bytes + p.numel() * p.element_size() > bucket_bytes or p.dtype != cur[0].dtype
+                        or p.device != cur[0].device):
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+        if cur:
+            groups.append(cur)
+        for bi, ps in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._of[p] = bi
+                self._handles.append(p.register_post_accumulate_grad_hook(self._ready))
+            self.buckets.append((flat, ps))
+            self._pending.append(len(ps))
+        backend = dist.get_backend(group)
+        self._avg = dist.ReduceOp.AVG if backend == "nccl" else None      # gloo has no AVG: divide afterwards
+
+    def zero(self) -> None:
+        """Replaces `optimizer.zero_grad(set_to_none=True)`: the views must survive."""
+        for bi, (flat, ps) in enumerate(self.buckets):
+            flat.zero_()
+            self._pending[bi] = len(ps)
+            off = 0
+            for p in ps:                                   # an optimiser / user may have dropped or replaced a view
+                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + off * flat.element_size():
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self._works = []
+
+    def _ready(self, p) -> None:
+        bi = self._of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            flat = self.buckets[bi][0]
+            if self._avg is not None:
+                self._works.append((dist.all_reduce(flat, op=self._avg, group=self.group, async_op=True), None))
+            else:
+                self._works.append((dist.all_reduce(flat, group=self.group, async_op=True), flat))
+
+    def finish(self) -> int:
+        """Wait for the bucket all-reduces launched during backward; reduce the buckets whose hooks never all fired
+        (parameters without a gradient this step).  Returns the number of elements exchanged."""
+        if self.ws == 1:
+            return 0
+        for bi, (flat, ps) in enumerate(self.buckets):
+            if self._pending[bi] > 0:                      # some gradients of the bucket were not produced: still exchange
+                self._pending[bi] = 0
+                self._works.append((dist.all_reduce(flat, group=self.group, async_op=True), flat))
+        n = 0
+        for work, flat in self._works:
+            work.wait()
+            if flat is not None:
+                flat.div_(self.ws)
+        for flat, _ in self.buckets:
+            n += flat.numel()
+        self._works = []
+        return n
+
+
 class DataParallelVQTrainer:
     """Minimal data-parallel trainer for a model whose forward returns the reference's dict
     (`{'recon', 'commit_loss', 'ids', ...}`, `vqwnet.py:147-152`).
@@ -75,18 +159,25 @@ class DataParallelVQTrainer:
         self.group = group
         self.commit_weight = commit_weight
         broadcast_module_state(model, 0, group)
+        for mod in model.modules():                       # global-batch EMA statistics: replicas stay bit-identical
+            if hasattr(mod, "reduce_mode") and hasattr(mod, "embed_avg"):
+                mod.reduce_mode = "sum"
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(self.params, lr=lr)
         self.world_size = _world(group)
+        self.buckets = GradientBuckets(self.params, group)
 
     def training_step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
         self.model.train(True)
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.world_size > 1:
+            self.buckets.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         out = self.model(images)
         recon_loss = F.mse_loss(out["recon"], images)
         loss = recon_loss + self.commit_weight * out["commit_loss"]
-        loss.backward()
-        all_reduce_gradients(self.params, self.group, average=True)
+        loss.backward()                                   # bucket all-reduces are launched from inside the backward
+        self.buckets.finish()
         self.optimizer.step()
         return {"loss": loss.detach(), "recon_loss": recon_loss.detach(), "commit_loss": out["commit_loss"].detach(),
                 "ids": out.get("ids")}

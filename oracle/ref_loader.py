@@ -9,9 +9,12 @@ kmeans_pytorch, none of which exist in this image.  We pr
                         directory (so `networks/__init__.py` is skipped but submodules
                         import normally),
   * `kmeans_pytorch` -> a dummy.
-No reference file is copied or modified.  `/root/reference` does not exist on the GPU
-box, so nothing that runs there may call this; it is used only by
-`oracle/make_golden.py` and by CPU tests that skip when the reference is absent.
+No reference file is modified.  `/root/reference` does not exist on the GPU box; `__graft_entry__.build()`
+therefore mirrors the reference's `src/` tree into the git-ignored `baseline/_ref/src/` whenever
+`/root/reference` is present (the directory travels to the GPU box with the snapshot like the built `.so`,
+and never enters the history).  Search order: `$VQ_REF_SRC`, `/root/reference/src`, `baseline/_ref/src`.
+Used by `oracle/make_golden*.py`, by tests that skip when no copy of the reference is reachable, and by
+`bench.py --impl reference` / the `cpu_baseline` leg (the reference's own module on the host cores).
 """
 from __future__ import annotations
 
@@ -20,7 +23,20 @@ import os
 import sys
 import types
 
-REF_SRC_CANDIDATES = [os.environ.get("VQ_REF_SRC", ""), "/root/reference/src"]
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_MIRROR = os.path.join(_REPO, "baseline", "_ref", "src")
+REF_SRC_CANDIDATES = [os.environ.get("VQ_REF_SRC", ""), "/root/reference/src", REF_MIRROR]
+
+
+def mirror_reference(src: str = "/root/reference/src") -> bool:
+    """Copy the reference's python sources into baseline/_ref/src (git-ignored) so that they travel to the GPU box.
+    Returns True when the mirror exists afterwards."""
+    import shutil
+    if os.path.isfile(os.path.join(src, "networks", "vq", "vq_module.py")):
+        if os.path.isdir(REF_MIRROR):
+            shutil.rmtree(REF_MIRROR)
+        shutil.copytree(src, REF_MIRROR, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    return os.path.isfile(os.path.join(REF_MIRROR, "networks", "vq", "vq_module.py"))
 
 
 def reference_src():
@@ -55,7 +71,7 @@ def load_reference_vq():
     """Returns the reference `VQModule` class (vq/vq_module.py:139)."""
     src = reference_src()
     if src is None:
-        raise RuntimeError("reference sources not present (expected /root/reference/src)")
+        raise RuntimeError("reference sources not present (expected /root/reference/src or baseline/_ref/src)")
     _install_stubs(src)
     return importlib.import_module("networks.vq.vq_module").VQModule
 
@@ -64,6 +80,6 @@ def load_reference_net(name: str):
     """`load_reference_net('vqwnet').VQWNet`, `('unet_encoder').UNetEncoder`, ..."""
     src = reference_src()
     if src is None:
-        raise RuntimeError("reference sources not present (expected /root/reference/src)")
+        raise RuntimeError("reference sources not present (expected /root/reference/src or baseline/_ref/src)")
     _install_stubs(src)
     return importlib.import_module("networks." + name)

@@ -40,7 +40,20 @@ def assert_ids_match(ids_gpu, ids_ref, embed, z, allow_ties=True):
     tie = score_gap_is_tie(embed.cpu(), flat[bad], a[bad], b[bad])
     assert bool(tie.all()), f"{int((~tie).sum())} id mismatches that are not fp32 ties (of {bad.numel()} differing rows)"
     assert bad.numel() <= max(2, a.numel() // 100000), f"too many tie rows: {bad.numel()}"
+    report_ties(int(bad.numel()), a.numel())
     return int(bad.numel())
+
+
+def report_ties(n, total, where=""):
+    """A differing row is tolerated only when the oracle's own fp32 scores of the two codes tie; say how many there
+    were (expected: 0), so that a regression from 0 is visible (`pytest -s`, or gpurun_out/parity_ties.log)."""
+    import os
+    msg = f"[parity] {n} tolerated tie rows of {total} {where}".rstrip()
+    print(msg)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if n and os.path.isdir(out):
+        with open(os.path.join(out, "parity_ties.log"), "a") as f:
+            f.write(msg + "\n")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -429,6 +442,41 @@ def test_full_size_properties(K, D, flags):
     assert torch.equal(ids2, ids) and loss2.item() == 0.0
 
 
+FULL_SIZE = [(512, 64, "gauss"), (512, 64, "clustered"), (512, 64, "relu"),
+             (512, 256, "gauss"), (512, 256, "clustered"), (512, 256, "relu")]
+
+
+@pytest.mark.parametrize("K,D,kind", FULL_SIZE)
+def test_full_size_vs_oracle(K, D, kind):
+    """BASELINE config 2 (N = 1 048 576, K = 512, D = 64) and the north-star point (K = 512, D = 256) against the CPU
+    oracle itself (chunked over N, same per-element arithmetic as the reference, vq_module.py:45-62): ids and counts
+    bit-exact, q bit-exact, loss and EMA buffers <= 1e-5 (max-norm relative, tests/util.py:rel_err).  The rare candidate
+    misses of a low-precision search only show up at this scale."""
+    B, H = 16, 256
+    N = B * H * H
+    z, embed = seeded_case(B, D, H, H, K, seed=4242 + D, kind=kind)
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=N, chunk=65536)
+    m = new_vq(K, D, 0.99, 0)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    ora.train(True)
+    m.train(True)
+    embed0 = ora.embed.clone()
+    with torch.no_grad():
+        q_ref, loss_ref, ids_ref = ora(z)
+        q, loss, ids = m(z.to(DEV))
+    torch.cuda.synchronize()
+    nties = assert_ids_match(ids, ids_ref, embed0, z)
+    report_ties(nties, N, f"(full size K={K} D={D} {kind})")
+    assert abs(loss.item() - loss_ref.item()) <= TOL * abs(loss_ref.item())
+    if nties == 0:
+        assert torch.equal(q.cpu(), q_ref.contiguous()), "quantized must be bit-exact"
+        counts = torch.bincount(ids.reshape(-1), minlength=K).cpu()
+        assert torch.equal(counts, torch.bincount(ids_ref.reshape(-1), minlength=K)), "histogram must be bit-exact"
+        assert rel_err(m.cluster_size, ora.cluster_size) <= TOL
+        assert rel_err(m.embed_avg, ora.embed_avg) <= TOL
+        assert rel_err(m.embed, ora.embed) <= TOL
+
+
 def test_simt_and_auto_paths_agree_at_full_size():
     B, D, H, K = 16, 64, 256, 512
     gen = torch.Generator(device=DEV).manual_seed(99)
@@ -552,6 +600,44 @@ def test_multistep_cold_training_paths_agree():
         with torch.no_grad():                       # keep the two replicas bit-identical for the next step
             for a, b in zip(ms[1].buffers(), ms[0].buffers()):
                 a.copy_(b)
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("n_micro", [2, 4])
+def test_micro_batch_accumulation_equals_one_big_batch(n_micro, flags):
+    """`accumulate_steps=n` (BASELINE config 5 at 2 / 4 GPUs: 64 / 32 slices of 512^2 per GPU do not fit one forward of
+    the full network): n training forwards on the n micro-batches == ONE forward of the oracle on the concatenated
+    batch -- ids / counts bit-exact, buffers <= 1e-5; the codebook must not move before the last micro-batch."""
+    B, D, H, K = 8, 64, 32, 512
+    z, embed = seeded_case(B, D, H, H, K, seed=515 + n_micro, kind="clustered")
+    ora = make_oracle(K, D, embed, warmed=True, n_for_warm=B * H * H)
+    ora.train(True)
+    m = new_vq(K, D, 0.99, flags, accumulate_steps=n_micro)
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    m.train(True)
+    embed0 = m.embed.clone()
+    with torch.no_grad():
+        _, loss_ref, ids_ref = ora(z)
+    mb = B // n_micro
+    ids_parts, losses = [], []
+    for i in range(n_micro):
+        zi = z[i * mb:(i + 1) * mb].to(DEV).requires_grad_(True)
+        q, loss, ids = m(zi)
+        (g,) = torch.autograd.grad(q.sum() + loss, zi)
+        ids_parts.append(ids.cpu())
+        losses.append(loss.item())
+        if i < n_micro - 1:
+            assert torch.equal(m.embed, embed0), "the codebook moved before the last micro-batch"
+    assert torch.equal(torch.cat(ids_parts), ids_ref)
+    assert abs(sum(losses) / n_micro - loss_ref.item()) <= TOL * abs(loss_ref.item())
+    assert rel_err(m.cluster_size, ora.cluster_size) <= TOL
+    assert rel_err(m.embed_avg, ora.embed_avg) <= TOL
+    assert rel_err(m.embed, ora.embed) <= TOL
+    # a partial accumulation is applied by flush_ema(); nothing is pending afterwards
+    m(z[:mb].to(DEV))
+    before = m.cluster_size.clone()
+    assert m.flush_ema() and not torch.equal(m.cluster_size, before)
+    assert not m.flush_ema()
 
 
 def test_embed_avg_layouts():
