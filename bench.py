@@ -2,8 +2,8 @@
 """bench.py -- headline benchmark of the B200 VQ bottleneck (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
-    python bench.py --sweep                                   # config-3 microbench table -> stderr/file
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own module on the host cores
+    python bench.py --workload vqwnet512 --gpus N ...        # BASELINE config 5: 128 slices of 512 x 512, data parallel
 
 A "step" is one pass of the hot path over one batch of synthetic input: the quantiser's training step
 (nearest-code search + gather + commitment loss + EMA statistics/update [+ packed all-reduce when
@@ -15,8 +15,11 @@ One JSON line on stdout (rank 0).  `value` = whole-job lookups/s with inputs res
 CUDA graphs of the step; `eager` = the same loop launched from Python, `--no-graphs` makes that the timed region);
 `e2e` = the same through the module's public API with HOST (pinned) input and the result (loss +
 code map) read back every step; `roofline` = the dominant kernel (nearest-code search) against the
-measured HBM peak; `cpu_baseline` = the oracle (a port of the reference's torch op chain) on the
-host cores, bounded sample.  `vqwnet_train` = the other half of BASELINE's metric: VQ-W-Net training slices/s
+measured HBM peak; `cpu_baseline` = the reference's own `VQModule` (git-ignored mirror baseline/_ref/src made by
+`__graft_entry__.build()`; the oracle port when no copy is reachable) on the host cores, bounded sample; `north_star` =
+the K = 512, D = 256 point (eval and train, clustered / ReLU / Gaussian input) with its own roofline fractions;
+`parity_check` = TC-vs-CUDA-core ids on one buffer and, for N > 1, the all-reduced statistics against the gathered
+local ones.  `vqwnet_train` = the other half of BASELINE's metric: VQ-W-Net training slices/s
 (BASELINE config 2: batch 16 of 256x256 slices per GPU, tools/wnet.py around this repo's quantiser, stock cuDNN
 convolutions, Adam), device-resident and end-to-end, measured after the headline region; `--workload vqwnet`
 makes it the line's own metric (and `--impl reference --workload vqwnet` times the same network on the host cores).
@@ -125,12 +128,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference op chain on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_step_factory(wl, slices):
+def cpu_quantiser(D, K):
+    """(module, kind): the UNMODIFIED reference `VQModule` (vq_module.py:139-211) when a copy of the reference is
+    reachable (/root/reference/src here, the git-ignored mirror baseline/_ref/src on the GPU box), else the oracle port."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            VQ = ref_loader.load_reference_vq()
+            return VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch"), "reference"
+    except Exception:
+        pass
     from oracle.vq_oracle import OracleVQ
+    return OracleVQ(D, K, CFG["momentum"], CFG["eps"], "torch", chunk=65536), "port"
+
+
+def cpu_step_factory(wl, slices):
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(1234)
     D, H, K = wl["D"], wl["H"], wl["K"]
-    m = OracleVQ(D, K, CFG["momentum"], CFG["eps"], "torch", chunk=65536)
+    m, kind = cpu_quantiser(D, K)
     m.train(True)
     with torch.no_grad():       # same warmed EMA state as the B200 arm
         cs = torch.rand(K, generator=torch.Generator().manual_seed(1234)) * (slices * H * H / K) + 1.0
@@ -148,6 +164,7 @@ def cpu_step_factory(wl, slices):
         torch.autograd.grad((q, loss), z, (g_q, one))
         return loss
 
+    step.kind = kind
     return step, slices * H * H
 
 
@@ -161,9 +178,10 @@ def run_cpu_baseline(wl, budget_s=12.0, slices=1):
         step()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": step.kind,
             "sample": f"{slices} slice(s) of the workload ({n} lookups) per step, quantiser train step "
-                      f"(fwd+EMA+bwd) on CPU, median of {len(times)} steps, {med * 1e3:.1f} ms/step"}
+                      f"(fwd+EMA+bwd) of {'the unmodified reference VQModule' if step.kind == 'reference' else 'the oracle port'} "
+                      f"on the host cores, median of {len(times)} steps, {med * 1e3:.1f} ms/step"}
 
 
 def run_reference_arm(args, wl, wl_name):
@@ -173,8 +191,22 @@ def run_reference_arm(args, wl, wl_name):
     # rank 0 alone times the CPU path: the reference gates its all_reduce on $WORLD_SIZE (utils/__init__.py:109-114),
     # which torchrun sets for the N > 1 launches -- this leg is a single process without a process group
     os.environ["WORLD_SIZE"] = "1"
+    # bounded sample: as many of the workload's slices per step as keep the whole run near two minutes (the reference
+    # materialises K x N scores and two N x K one-hot matrices per call: ~9 GB and seconds per step at the full 16 slices)
     slices = 2
     step, n = cpu_step_factory(wl, slices)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_slice = (time.perf_counter() - t0) / slices
+    budget = float(os.environ.get("VQ_REF_BUDGET_S", 120.0))
+    want = slices
+    for cand in (4, 8, wl["B"]):
+        if cand <= wl["B"] and per_slice * cand * (args.steps + max(1, min(args.warmup, 2))) <= budget:
+            want = cand
+    if want != slices:
+        slices = want
+        step, n = cpu_step_factory(wl, slices)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -187,9 +219,11 @@ def run_reference_arm(args, wl, wl_name):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl, wl_name, args.gpus, extra={"reference_sample_slices_per_step": slices}),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{slices} slices ({n} lookups) per step; oracle port of vq_module.py on host cores "
-                                   "(the reference is Python and cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": step.kind,
+                         "sample": f"{slices} of the workload's {wl['B']} slices ({n} lookups) per step; "
+                                   + ("the unmodified reference VQModule (baseline/_ref mirror) on the host cores"
+                                      if step.kind == "reference" else "oracle port of vq_module.py on the host cores "
+                                      "(no copy of the reference reachable)")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -204,6 +238,132 @@ def workload_config(wl, wl_name, gpus, extra=None):
     if extra:
         c.update(extra)
     return c
+
+
+def load_traffic(key):
+    """(bytes, source) of a pre-recorded `ncu --set full` capture of this workload's search kernel, or (None, None).
+    The figure is NOT measured in this run: it is copied from profiles/traffic.json, which names the capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f).get(key)
+        if tj:
+            return tj["bytes"], f"pre-recorded ncu capture {tj.get('source', '?')} via profiles/traffic.json (not measured in this run)"
+    except Exception:
+        pass
+    return None, None
+
+
+def kernel_time_ms(L, fn, launches, warm=2):
+    """Average CUDA-event time of the search kernel (library events on the launching stream) over `launches` calls."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    tot, nl = ctypes.c_double(0), ctypes.c_int(0)
+    L.vq_profile_enable(1)
+    L.vq_profile_read(None, None)
+    for i in range(launches):
+        fn(warm + i)
+    torch.cuda.synchronize()
+    L.vq_profile_read(ctypes.byref(tot), ctypes.byref(nl))
+    L.vq_profile_enable(0)
+    return (tot.value / nl.value) if nl.value else None
+
+
+def measure_north_star(dev, L, pkg, launches=6):
+    """The north-star point of BASELINE.json: fused quantiser at K = 512, D = 256, N = 1 048 576 on one GPU, eval and
+    train instantiations of the search kernel, on the three synthetic inputs of SURVEY 8(d)."""
+    B, D, H, K = 16, 256, 256, 512
+    N = B * H * H
+    hbm, bf16, which = measured_peaks()
+    alg_bytes = N * (8 * D + 8)
+    alg_flops = 2.0 * K * D * N
+    t_hbm, t_tc = alg_bytes / (hbm * 1e9), alg_flops / (bf16 * 1e12)
+    out = {"workload": f"k512d256: z = {B}x{D}x{H}x{H} fp32, K = {K}", "algorithmic_bytes_per_launch": alg_bytes,
+           "algorithmic_flops_per_launch": alg_flops, "roofline_ms": max(t_hbm, t_tc) * 1e3,
+           "bound": "hbm" if t_hbm >= t_tc else "tensor", "peak_source": f"MEASURED_PEAKS.json ({which})", "cases": {}}
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    vq = pkg.VQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch").to(dev)
+    embed0 = vq.embed.detach().clone()
+    cs0 = (torch.rand(K, generator=torch.Generator().manual_seed(1234)) * (N / K) + 1.0).to(dev)
+
+    def reset():
+        with torch.no_grad():
+            vq.embed.copy_(embed0)
+            vq.cluster_size.copy_(cs0)
+            vq.embed_avg.copy_((embed0 * cs0[:, None]).T)
+
+    for kind in ("clustered", "relu", "gauss"):
+        if kind == "clustered":
+            mk = lambda: (embed0[torch.randint(0, K, (B, H, H), device=dev, generator=gen)].permute(0, 3, 1, 2)
+                          + 0.1 * torch.randn(B, D, H, H, device=dev, generator=gen)).contiguous()
+        elif kind == "relu":
+            mk = lambda: torch.relu(torch.randn(B, D, H, H, device=dev, generator=gen))
+        else:
+            mk = lambda: torch.randn(B, D, H, H, device=dev, generator=gen)
+        zs = [mk() for _ in range(2)]                       # 2 x 1 GB: every launch reads a buffer >> L2
+        case = {}
+        for mode in ("eval", "train"):
+            reset()
+            vq.train(mode == "train")
+            with torch.no_grad():
+                ms = kernel_time_ms(L, lambda i: vq(zs[i % 2]), launches)
+            traffic, src = load_traffic(f"k512d256_{mode}_{kind}")
+            ach = alg_bytes / (ms * 1e-3) / 1e9 if ms else None
+            case[mode] = {"kernel_ms": ms, "achieved_gbs": ach, "frac": (max(t_hbm, t_tc) * 1e3 / ms) if ms else None,
+                          "traffic": traffic, "traffic_source": src}
+        out["cases"][kind] = case
+        del zs
+        torch.cuda.empty_cache()
+    return out
+
+
+def parity_self_check(dev, L, vq, z, world):
+    """Outside the timed region: (a) the tensor-core search and the CUDA-core search give the same code map on one
+    buffer; (b) N > 1: the all-reduced packed statistics equal the sum of the all-gathered local ones (counts bit for
+    bit; the fp32 sums to 1e-6 -- NCCL's reduction order is not the gather order)."""
+    import torch.distributed as dist
+    res = {}
+    was_training, flags = vq.training, vq.kernel_flags
+    vq.eval()
+    with torch.no_grad():
+        vq.kernel_flags = 0
+        ids_a = vq(z)[2].clone()
+        vq.kernel_flags = 1
+        ids_b = vq(z)[2].clone()
+    vq.kernel_flags = flags
+    vq.train(was_training)
+    res["tc_vs_simt_ids_equal"] = bool(torch.equal(ids_a, ids_b))
+    ok = res["tc_vs_simt_ids_equal"]
+    if world > 1:
+        B, D, H, W = z.shape
+        K = vq.embed.shape[0]
+        n = B * H * W
+        stats = torch.empty(L.vq_stats_floats(K, D), dtype=torch.float32, device=dev)
+        q = torch.empty_like(z)
+        ids = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = torch.empty(L.vq_workspace_bytes(n, K, D), dtype=torch.uint8, device=dev)
+        rc = L.vq_assign_fwd(z.detach().data_ptr(), B, D, H, W, vq.embed.data_ptr(), K, ids.data_ptr(), None, q.data_ptr(),
+                             loss.data_ptr(), stats.data_ptr(), None, ws.data_ptr(), ws.numel(), 0,
+                             torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, L.vq_last_error()
+        gathered = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, stats)
+        total = gathered[0].clone()
+        for g_ in gathered[1:]:
+            total += g_
+        reduced = stats.clone()
+        dist.all_reduce(reduced)
+        off = L.vq_stats_sums_offset(K)
+        res["counts_bit_exact"] = bool(torch.equal(reduced[:off], total[:off]))
+        denom = total[off:].abs().max().clamp_min(1e-30)
+        res["sums_max_rel"] = float(((reduced[off:] - total[off:]).abs().max() / denom).item())
+        ok = ok and res["counts_bit_exact"] and res["sums_max_rel"] <= 1e-6
+        okt = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = bool(okt.item() > 0.5)
+    res["ok"] = ok
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -408,6 +568,17 @@ def run_b200_arm(args, wl, wl_name):
             if wsb is not None:
                 fb_rows = int(L.vq_debug_fallback_rows(wsb.data_ptr(), n_per_gpu, K, D, torch.cuda.current_stream().cuda_stream))
     vq.train(True)
+    parity = parity_self_check(dev, L, vq, zbufs[0].detach(), world)
+
+    # ---- the north-star point (K = 512, D = 256) on one GPU, outside the headline regions -------------------------
+    north = None
+    if world == 1 and wl_name == "config2" and not args.no_north_star:
+        for t_ in zbufs[1:]:
+            t_.grad = None
+        try:
+            north = measure_north_star(dev, L, pkg)
+        except Exception as exc:
+            north = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- the other half of BASELINE's metric: VQ-W-Net train slices/s (after, and outside, the headline regions) ----
     wnet = None
@@ -437,19 +608,17 @@ def run_b200_arm(args, wl, wl_name):
             else:
                 ach = alg_flops / (avg_kernel_ms * 1e-3) / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16}
-            traffic = None
-            try:        # measured DRAM bytes per launch of this workload's search kernel (one ncu --set full capture)
-                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    tj = json.load(f).get(wl_name)
-                if tj and path == 1:
-                    traffic = tj["bytes"]
-            except Exception:
-                traffic = None
-            roof.update({"traffic": traffic, "kernel": {1: "vq_assign_tc", 2: "vq_assign_small"}.get(path, "vq_assign_simt"),
+            traffic, traffic_src = load_traffic(wl_name) if path == 1 else (None, None)
+            roof.update({"traffic": traffic, "traffic_source": traffic_src, "kernel": {1: "vq_assign_tc", 2: "vq_assign_small"}.get(path, "vq_assign_simt"),
                          "kernel_ms": avg_kernel_ms, "launches_timed": nl.value,
                          "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                          "peak_source": f"MEASURED_PEAKS.json ({which})"})
         cpu = run_cpu_baseline(wl) if (world == 1 and not args.no_cpu) else None
+        if isinstance(wnet, dict) and "error" not in wnet and world == 1 and not args.no_cpu:
+            try:
+                wnet["cpu_baseline"] = run_cpu_wnet_baseline(budget_s=12.0)
+            except Exception as exc:
+                wnet["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -463,6 +632,7 @@ def run_b200_arm(args, wl, wl_name):
                                                                      if use_graphs else (graph_note or "eager loop (--no-graphs)"))}),
             "e2e": {"value": world * n_per_gpu * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": z_host[0].numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
+                    "returned": "code map (int64) + loss; quantized and the input gradient stay on the device",
                     "overlap": "step i+1 H2D (copy stream, double buffer) overlaps step i kernels; result read every step",
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
@@ -472,6 +642,8 @@ def run_b200_arm(args, wl, wl_name):
             "eval_forward": {"value": world * n_per_gpu / (eval_ms * 1e-3), "unit": UNIT, "ms_per_step": eval_ms,
                              "fallback_rows": fb_rows},
             "eager": {"value": world * n_per_gpu * args.steps / (eager_ms * 1e-3), "unit": UNIT, "ms_per_step": eager_ms / args.steps},
+            "parity_check": parity,
+            "north_star": north,
             "vqwnet_train": wnet,
         }
         print(json.dumps(out), flush=True)
@@ -494,11 +666,26 @@ WNET_METRIC = "vqwnet_train_slices_per_s"
 WNET_UNIT = "slices/s"
 
 
-def wnet_config(gpus, extra=None):
-    c = {"workload": f"vqwnet: VQ-W-Net training step (tools/wnet.py = vqwnet.py topology, filters 64..1024, K = {WNET['K']}; "
-                     f"loss = mse(recon, x) + commit_loss, Adam lr 1e-4), batch {WNET['B']} of 1x{WNET['H']}x{WNET['H']} "
-                     "synthetic slices per GPU, fp32 (cuDNN convolutions at torch's default: TF32 allowed)",
-         "slices_per_gpu": WNET["B"], "resolution": WNET["H"], "dict_size": WNET["K"], "emb_dim": WNET["D"],
+WNET512_GLOBAL = 128          # BASELINE config 5: batch 128 of 512 x 512 slices over the GPUs of one box
+WNET512_MICRO = 16            # slices per forward (one micro-batch); 16 x 512^2 through the full-resolution double U-Net
+
+
+def wnet_shape(name, world):
+    """(slices per GPU per step, resolution, micro-batches per step)"""
+    if name == "vqwnet512":
+        per_gpu = WNET512_GLOBAL // world
+        return per_gpu, 512, max(1, per_gpu // WNET512_MICRO)
+    return WNET["B"], WNET["H"], 1
+
+
+def wnet_config(gpus, extra=None, name="vqwnet"):
+    B, H, micro = wnet_shape(name, gpus)
+    c = {"workload": f"{name}: VQ-W-Net training step (tools/wnet.py = vqwnet.py topology, filters 64..1024, K = {WNET['K']}; "
+                     f"loss = mse(recon, x) + commit_loss, Adam lr 1e-4), batch {B} of 1x{H}x{H} "
+                     "synthetic slices per GPU, fp32 (cuDNN convolutions at torch's default: TF32 allowed)"
+                     + (f"; global batch {WNET512_GLOBAL} (run_vqwnet.py:112-121), {micro} micro-batch(es) of {B // micro} slices per "
+                        "step with gradients and EMA statistics accumulated, exchanged once" if name == "vqwnet512" else ""),
+         "slices_per_gpu": B, "resolution": H, "dict_size": WNET["K"], "emb_dim": WNET["D"], "micro_batches": micro,
          "parallelism": f"dp{gpus}", "l2": "a step streams > 10 GB of activations (>> 126 MB L2)"}
     if extra:
         c.update(extra)
@@ -511,7 +698,7 @@ def wnet_images(n, B, H, seed, pin=False):
     return [t.pin_memory() for t in out] if pin else out
 
 
-def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
+def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, name="vqwnet"):
     """VQ-W-Net train slices/s on this rank's GPU (data parallel over `world` ranks).  Returns a dict on rank 0."""
     import torch.distributed as dist
     import medical_image_editing_b200 as pkg
@@ -520,7 +707,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     from wnet import WNetHarness
 
     L = pkg.lib()
-    B, H = WNET["B"], WNET["H"]
+    B, H, micro = wnet_shape(name, world)
     torch.manual_seed(0)
     model = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch",
                                             reduce_mode="sum", overlap_exchange=(world > 1 and not inline_exchange)),
@@ -541,7 +728,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
         return float(t.item())
 
     for i in range(warmup):
-        trainer.training_step(resident[i % 4])
+        trainer.training_step(resident[i % 4], micro_batches=micro)
     barrier()
     L.vq_profile_enable(1)
     L.vq_profile_read(None, None)
@@ -549,7 +736,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        trainer.training_step(resident[i % 4])
+        trainer.training_step(resident[i % 4], micro_batches=micro)
     e1.record()
     barrier()
     ms = maxed(e0.elapsed_time(e1))
@@ -566,7 +753,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     s0.record()
     for i in range(steps):
         dev_in.copy_(host[i % 4], non_blocking=True)
-        out = trainer.training_step(dev_in)
+        out = trainer.training_step(dev_in, micro_batches=micro)
         losses.append(float(out["loss"].item()))
     s1.record()
     barrier()
@@ -577,12 +764,12 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     if rank != 0:
         return None
     hbm, _, which = measured_peaks()
-    n_vec = B * H * H
+    n_vec = (B // micro) * H * H                             # vectors per quantiser call
     alg_bytes = n_vec * (8 * WNET["D"] + 8)
     k_ms = (tot_ms.value / nl.value) if nl.value else None
     return {
         "metric": WNET_METRIC, "value": world * B * steps / (ms * 1e-3), "unit": WNET_UNIT, "ms_per_step": ms / steps,
-        "steps": steps, "warmup": warmup, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "n_gpus": world, "slices_per_gpu": B, "resolution": H, "micro_batches": micro,
         "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": WNET_UNIT, "h2d_bytes_per_step": B * H * H * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
         "gpu_launches": int(launches),
@@ -594,16 +781,28 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False):
     }
 
 
-def cpu_wnet_step_factory(slices):
-    from oracle.vq_oracle import OracleVQ
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from wnet import WNetHarness
+def cpu_wnet_step_factory(slices, H=None):
+    """One Adam step of VQ-W-Net on the host cores: the UNMODIFIED reference `VQWNet` (vqwnet.py:13-152, with its own
+    `VQModule`) when a copy of the reference is reachable, else tools/wnet.py around the oracle quantiser."""
+    H = H or WNET["H"]
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    model = WNetHarness(lambda d, k: OracleVQ(d, k, 0.99, 1e-5, "torch", chunk=65536), 1, dict_size=WNET["K"])
+    model, kind = None, "port"
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            model = ref_loader.load_reference_net("vqwnet").VQWNet(1, 1, dict_size=WNET["K"])
+            kind = "reference"
+    except Exception:
+        model = None
+    if model is None:
+        from oracle.vq_oracle import OracleVQ
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from wnet import WNetHarness
+        model = WNetHarness(lambda d, k: OracleVQ(d, k, 0.99, 1e-5, "torch", chunk=65536), 1, dict_size=WNET["K"])
     model.train(True)
     opt = torch.optim.Adam(model.parameters(), lr=WNET["lr"])
-    imgs = wnet_images(2, slices, WNET["H"], 4321)
+    imgs = wnet_images(2, slices, H, 4321)
     state = {"i": 0}
 
     def step():
@@ -616,11 +815,12 @@ def cpu_wnet_step_factory(slices):
         opt.step()
         return loss
 
+    step.kind = kind
     return step
 
 
-def run_cpu_wnet_baseline(budget_s=15.0, slices=1):
-    step = cpu_wnet_step_factory(slices)
+def run_cpu_wnet_baseline(budget_s=15.0, slices=1, H=None):
+    step = cpu_wnet_step_factory(slices, H)
     step()
     times = []
     t_all = time.perf_counter()
@@ -629,9 +829,11 @@ def run_cpu_wnet_baseline(budget_s=15.0, slices=1):
         step()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": slices / med, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{slices} slice(s) per step: tools/wnet.py with the CPU oracle quantiser (bit-identical to the reference "
-                      f"VQWNet on CPU, tests/test_wnet_harness.py), median of {len(times)} steps, {med * 1e3:.0f} ms/step"}
+    return {"value": slices / med, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": step.kind,
+            "sample": f"{slices} slice(s) of {H or WNET['H']}^2 per step: "
+                      + ("the unmodified reference VQWNet (baseline/_ref mirror) on the host cores" if step.kind == "reference" else
+                         "tools/wnet.py with the CPU oracle quantiser (bit-identical to the reference VQWNet on CPU, tests/test_wnet_harness.py)")
+                      + f", median of {len(times)} steps, {med * 1e3:.0f} ms/step"}
 
 
 def run_wnet_reference_arm(args):
@@ -639,7 +841,8 @@ def run_wnet_reference_arm(args):
         return
     os.environ["WORLD_SIZE"] = "1"
     slices = 1
-    step = cpu_wnet_step_factory(slices)
+    _, H, _ = wnet_shape(args.workload, max(1, args.gpus))
+    step = cpu_wnet_step_factory(slices, H)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -649,11 +852,13 @@ def run_wnet_reference_arm(args):
     val = slices * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": WNET_METRIC, "value": val, "unit": WNET_UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "vqwnet512" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": wnet_config(args.gpus, extra={"reference_sample_slices_per_step": slices}),
-        "cpu_baseline": {"value": val, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{slices} slice per step; VQ-W-Net topology with the oracle quantiser on the host cores"},
+        "config": wnet_config(args.gpus, extra={"reference_sample_slices_per_step": slices}, name=args.workload),
+        "cpu_baseline": {"value": val, "unit": WNET_UNIT, "cores": torch.get_num_threads(), "kind": step.kind,
+                         "sample": f"{slices} slice of {H}^2 per step; " + ("the unmodified reference VQWNet" if step.kind == "reference"
+                                                                          else "VQ-W-Net topology with the oracle quantiser") + " on the host cores"},
         "e2e": {"value": val, "unit": WNET_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -670,14 +875,16 @@ def run_wnet_b200_arm(args):
     dev = torch.device("cuda", local)
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
-    r = measure_wnet_b200(dev, rank, world, args.steps, args.warmup, args.inline_exchange)
+    r = measure_wnet_b200(dev, rank, world, args.steps, args.warmup, args.inline_exchange, name=args.workload)
     t1 = time.time()
     if rank == 0:
         clocks = sampler.stop(t0, t1)
-        cpu = run_cpu_wnet_baseline() if (world == 1 and not args.no_cpu) else None
+        _, H, _ = wnet_shape(args.workload, world)
+        cpu = run_cpu_wnet_baseline(H=H) if (world == 1 and not args.no_cpu) else None
         out = {"metric": WNET_METRIC, "value": r["value"], "unit": WNET_UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wnet_config(world),
+               "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong" if args.workload == "vqwnet512" else "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wnet_config(world, name=args.workload),
                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": r["roofline"],
                "cpu_baseline": cpu, "replicas_in_sync": r["replicas_in_sync"], "final_loss": r["final_loss"]}
         print(json.dumps(out), flush=True)
@@ -691,8 +898,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["vqwnet"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["vqwnet", "vqwnet512"])
     ap.add_argument("--no-model", action="store_true", help="skip the VQ-W-Net train slices/s block of the default line")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the K = 512, D = 256 block of the default line")
     ap.add_argument("--simt", action="store_true", help="force the fp32 CUDA-core search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
@@ -700,7 +908,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="eager step loop in the timed region instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.workload == "vqwnet":
+    if args.workload in ("vqwnet", "vqwnet512"):
         return run_wnet_reference_arm(args) if args.impl == "reference" else run_wnet_b200_arm(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -44,6 +44,12 @@ typedef void* vq_stream_t;
                                      half of every codebook slice) instead of one CTA per tile; same results, not
                                      faster on B200 -- kept for A/B timing */
 
+#define VQ_FLAG_IDS_NATURAL  16   /* `ids` (int64) is written in natural (b, h, w) order instead of the reference's
+                                     (b, w, h) order (vq_module.py:171,178): what every caller builds next with
+                                     transpose(ids, 1, 2) (vqwnet.py:110, unet_encoder.py:115)                 */
+#define VQ_FLAG_IDS_ONE_BASED 32  /* `ids` (int64) holds code + 1: the callers' `ids += 1` (vqwnet.py:111) folded
+                                     into the epilogue; `ids_nat` (int32, for vq_bwd) stays 0-based            */
+
 /* vq_lookup layouts */
 #define VQ_LAYOUT_ROWS        0   /* out[n, D]  (F.embedding layout, vq_module.py:203-206)  */
 #define VQ_LAYOUT_NCHW_T      1   /* ids [B,A,C] -> out [B,D,C,A]  contiguous: the tensor the

@@ -19,6 +19,8 @@ VQ_FLAG_FORCE_SIMT = 1
 VQ_FLAG_FORCE_TC = 2
 VQ_FLAG_NO_STATS = 4
 VQ_FLAG_PAIR = 8
+VQ_FLAG_IDS_NATURAL = 16
+VQ_FLAG_IDS_ONE_BASED = 32
 VQ_LAYOUT_ROWS = 0
 VQ_LAYOUT_NCHW_T = 1
 

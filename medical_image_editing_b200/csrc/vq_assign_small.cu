@@ -23,7 +23,7 @@ template <int KMAX>
 __global__ void __launch_bounds__(SM_THREADS)
 vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
                        int B, int D, int H, int W, int K, int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat,
-                       float* __restrict__ q, double* __restrict__ loss_acc) {
+                       float* __restrict__ q, double* __restrict__ loss_acc, int ids_mode) {
   extern __shared__ __align__(16) float smem_f[];
   float* e_s = smem_f;                              // [D][KMAX]  transposed codebook, 0 for k >= K
   float* e2_s = e_s + (size_t)D * KMAX;             // [KMAX]     |e|^2, +inf for k >= K
@@ -53,7 +53,7 @@ vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E,
     float accA[KMAX], accB[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) { accA[k] = 0.f; accB[k] = 0.f; }
-    float z2 = 0.f;
+    float z2A = 0.f, z2B = 0.f;                  // |z|^2 = A + B like the dot products (vq_common.cuh)
     if (valid) {
       for (int j = 0; j < nq; j += 2) {
         float zv8[8];                               // all eight loads of this pair of quads in flight before any use
@@ -64,7 +64,8 @@ vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E,
           const int d = 4 * j + u;
           if (d < D) {
             const float zv = zv8[u];
-            z2 = __fmaf_rn(zv, zv, z2);
+            if (u < 4) z2A = __fmaf_rn(zv, zv, z2A);
+            else z2B = __fmaf_rn(zv, zv, z2B);
             const float4* er = reinterpret_cast<const float4*>(e_s + (size_t)d * KMAX);
 #pragma unroll
             for (int k4 = 0; k4 < KMAX / 4; ++k4) {
@@ -85,6 +86,7 @@ vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E,
         }
       }
     }
+    const float z2 = __fadd_rn(z2A, z2B);
     float best = -INFINITY;
     int bi = 0;
 #pragma unroll
@@ -96,7 +98,7 @@ vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E,
 
     if (valid) {
       const int h = p / W, w = p - h * W;
-      if (ids) ids[b * HW + (long long)w * H + h] = bi;
+      if (ids) store_id(ids + b * HW, p, h, w, H, bi, ids_mode);
       if (ids_nat) ids_nat[n] = bi;
     }
 
@@ -126,15 +128,7 @@ vq_assign_small_kernel(const float* __restrict__ z, const float* __restrict__ E,
   if (lane == 0 && loss_acc && lsum != 0.f) atomicAdd(loss_acc, (double)lsum);
 }
 
-static int small_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int small_sm_count() { return device_sm_count(); }
 
 int launch_assign_small(const FwdArgs& a, cudaStream_t s) {
   VQ_REQUIRE(small_path_supported(a.B, a.D, a.H, a.W, a.K) && a.stats == nullptr, VQ_ERR_UNSUPPORTED,
@@ -148,7 +142,7 @@ int launch_assign_small(const FwdArgs& a, cudaStream_t s) {
   if (blocks < 1) blocks = 1;
   const bool prof = profile_begin(s);
   vq_assign_small_kernel<KMAX><<<(unsigned)blocks, SM_THREADS, smem, s>>>(a.z, a.embed, a.ws.e2, a.B, a.D, a.H, a.W, a.K,
-                                                                          a.ids, a.ids_nat, a.q, a.ws.loss_acc);
+                                                                          a.ids, a.ids_nat, a.q, a.ws.loss_acc, ids_mode_of(a.flags));
   if (prof) profile_end(s);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());

@@ -33,6 +33,11 @@ const char* get_error();
     }                                                                                    \
   } while (0)
 
+// per-device launch state: one process may drive several GPUs (device index = cudaGetDevice() at the call)
+constexpr int kMaxDevices = 64;
+int current_device();                 // cudaGetDevice(), clamped to [0, kMaxDevices)
+int device_sm_count();                // multiprocessors of the current device (cached per device)
+
 // measurement hooks (vq_launch_count / vq_profile_*)
 void count_launch(int n = 1);
 long long launch_count();
@@ -131,6 +136,13 @@ int launch_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* la
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
+// ids_mode = (flags / VQ_FLAG_IDS_NATURAL) & 3: bit 0 natural (b, h, w) order, bit 1 one-based
+inline int ids_mode_of(int flags) { return (flags / VQ_FLAG_IDS_NATURAL) & 3; }
+// the int64 code map entry of pixel p = h * W + w of an image whose map starts at `img`: reference layout (b, w, h) and
+// 0-based by default (vq_module.py:171,178), or the (b, h, w) / 1-based form its callers build next (vqwnet.py:110-111)
+__device__ __forceinline__ void store_id(int64_t* img, long long p, int h, int w, int H, int id, int ids_mode) {
+  img[(ids_mode & 1) ? p : (long long)w * H + h] = (int64_t)(id + ((ids_mode >> 1) & 1));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -142,8 +154,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // `dot` is, in every kernel of this library (CUDA-core search, exhaustive fallback, tensor-core re-rank), the same
 // fp32 value: dot = fl(A + B) with A (B) the ascending-d fma chain over the channels whose quad index d >> 2 is even
 // (odd).  Two chains are what the two lanes of a pixel in the tensor-core kernels compute from their own registers;
-// identical summation order everywhere keeps the search paths bit-identical to each other.  |e|^2 and |z|^2 are single
-// ascending-d fma chains.
+// identical summation order everywhere keeps the search paths bit-identical to each other.  |z|^2 = fl(A' + B') is
+// split over the same two chains (the lanes of a pixel hold exactly those channels); |e|^2 is a single ascending-d chain.
 __device__ __forceinline__ float ref_score(float dot, float e2, float z2) {
   return __fsub_rn(__fmaf_rn(2.0f, dot, -e2), z2);
 }

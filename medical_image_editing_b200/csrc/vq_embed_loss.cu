@@ -257,15 +257,7 @@ vq_el_bwd_generic_kernel(const float* __restrict__ g_loss, const float* __restri
   for (int d = 0; d < D; ++d) g_z[base + (long long)d * HW] = coef * (z[base + (long long)d * HW] - __ldg(er + d));
 }
 
-static int el_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int el_sm_count() { return device_sm_count(); }
 
 int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* embed, int B, int D, int H, int W, int K,
                           float* loss, float* weights, void* work, cudaStream_t s) {

@@ -155,7 +155,7 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
                       const float* __restrict__ E, int B, int D, int H, int W, int K, int Kpad,
                       const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
                       int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat, float* __restrict__ q,
-                      double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums) {
+                      double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums, int ids_mode) {
   __shared__ __align__(16) float zs[SIMT_DC][SIMT_TP];
   __shared__ __align__(16) float es[SIMT_DC][SIMT_TK];
   __shared__ float e2s[SIMT_TK];
@@ -201,7 +201,7 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
 
     float best[4];
     int bidx[4];
-    float z2[4] = {0.f, 0.f, 0.f, 0.f};
+    float z2[4] = {0.f, 0.f, 0.f, 0.f}, z2B[4] = {0.f, 0.f, 0.f, 0.f};   // |z|^2 = A + B (even / odd channel quads)
 #pragma unroll
     for (int i = 0; i < 4; ++i) { best[i] = -INFINITY; bidx[i] = 0; }
 
@@ -239,12 +239,23 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
 
         const int dlim = min(SIMT_DC, D - d0);
         if (cb == 0) {
-          for (int dd = 0; dd < dlim; ++dd) {
+          for (int dd = 0; dd < dlim; ++dd) {              // d0 is a multiple of 32: quad parity = (dd >> 2) & 1
             const float4 zv = *reinterpret_cast<const float4*>(&zs[dd][tx * 4]);
-            z2[0] = __fmaf_rn(zv.x, zv.x, z2[0]);
-            z2[1] = __fmaf_rn(zv.y, zv.y, z2[1]);
-            z2[2] = __fmaf_rn(zv.z, zv.z, z2[2]);
-            z2[3] = __fmaf_rn(zv.w, zv.w, z2[3]);
+            if (((dd >> 2) & 1) == 0) {
+              z2[0] = __fmaf_rn(zv.x, zv.x, z2[0]);
+              z2[1] = __fmaf_rn(zv.y, zv.y, z2[1]);
+              z2[2] = __fmaf_rn(zv.z, zv.z, z2[2]);
+              z2[3] = __fmaf_rn(zv.w, zv.w, z2[3]);
+            } else {
+              z2B[0] = __fmaf_rn(zv.x, zv.x, z2B[0]);
+              z2B[1] = __fmaf_rn(zv.y, zv.y, z2B[1]);
+              z2B[2] = __fmaf_rn(zv.z, zv.z, z2B[2]);
+              z2B[3] = __fmaf_rn(zv.w, zv.w, z2B[3]);
+            }
+          }
+          if (d0 + SIMT_DC >= D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z2[i] = __fadd_rn(z2[i], z2B[i]);
           }
         }
         for (int d8 = 0; d8 < dlim; d8 += 8) {            // d0 is a multiple of 32: quad parity = (dd >> 2) & 1
@@ -304,7 +315,7 @@ vq_assign_simt_kernel(const float* __restrict__ z, const float* __restrict__ et,
         const long long b = off / ((long long)D * HW);
         const long long p = off - b * (long long)D * HW;
         const int h = (int)(p / W), w = (int)(p % W);
-        if (ids) ids[b * HW + (long long)w * H + h] = bi;
+        if (ids) store_id(ids + b * HW, p, h, w, H, bi, ids_mode);
         if (ids_nat) ids_nat[b * HW + p] = bi;
         if (counts) atomicAdd(&counts[bi], 1);
         const float* erow = E + (size_t)bi * D;
@@ -355,7 +366,7 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
                         const float* __restrict__ E, int D, int H, int W, int K, int Kpad,
                         const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
                         int64_t* __restrict__ ids, int32_t* __restrict__ ids_nat, float* __restrict__ q,
-                        double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums) {
+                        double* __restrict__ loss_acc, int* __restrict__ counts, float* __restrict__ sums, int ids_mode) {
   extern __shared__ float zr[];                       // [D]
   __shared__ float red_s[FB_THREADS / 32];
   __shared__ int red_i[FB_THREADS / 32];
@@ -372,8 +383,12 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
     __syncthreads();
     for (int d = tid; d < D; d += FB_THREADS) zr[d] = __ldg(z + off + (long long)d * HW);
     __syncthreads();
-    float z2 = 0.f;
-    for (int d = 0; d < D; ++d) z2 = __fmaf_rn(zr[d], zr[d], z2);
+    float z2 = 0.f, z2B = 0.f;                       // |z|^2 = A + B (even / odd channel quads, vq_common.cuh)
+    for (int d = 0; d < D; ++d) {
+      if (((d >> 2) & 1) == 0) z2 = __fmaf_rn(zr[d], zr[d], z2);
+      else z2B = __fmaf_rn(zr[d], zr[d], z2B);
+    }
+    z2 = __fadd_rn(z2, z2B);
     float best = -INFINITY;
     int bi = 0;
     for (int k0 = 0; k0 < Kpad; k0 += 2 * FB_THREADS) {     // two codes per thread in flight: k, k + 256
@@ -451,7 +466,7 @@ vq_fallback_rows_kernel(const float* __restrict__ z, const float* __restrict__ e
       if (!(best > -INFINITY)) bi = 0;                 // all-NaN row: the reference's topk returns index 0
       s_best = bi;
       const int h = (int)(p / W), w = (int)(p % W);
-      if (ids) ids[b * HW + (long long)w * H + h] = bi;
+      if (ids) store_id(ids + b * HW, p, h, w, H, bi, ids_mode);
       if (ids_nat) ids_nat[n] = bi;
       if (counts) atomicAdd(&counts[bi], 1);
     }
@@ -729,15 +744,24 @@ vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict
 // =============================================================================================
 // launchers
 // =============================================================================================
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
 }
+
+int device_sm_count() {
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
+static int sm_count() { return device_sm_count(); }
 
 int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s) {
   const int Kpad = pad_codes(a.K);
@@ -772,7 +796,7 @@ int launch_assign_simt(const FwdArgs& a, bool fallback_list_mode, cudaStream_t s
   vq_assign_simt_kernel<<<blocks, 256, 0, s>>>(a.z, a.ws.et, a.ws.e2, a.embed, a.B, a.D, a.H, a.W, a.K, Kpad,
                                                fallback_list_mode ? a.ws.fb_rows : nullptr, a.ws.misc,
                                                a.ids, a.ids_nat, a.q, a.ws.loss_acc,
-                                               a.stats ? a.ws.counts : nullptr, sums);
+                                               a.stats ? a.ws.counts : nullptr, sums, ids_mode_of(a.flags));
   if (prof) profile_end(s);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
@@ -786,13 +810,13 @@ int launch_fallback_rows(const FwdArgs& a, cudaStream_t s) {
   // short lists: one CTA per row (latency-bound, finishes in a few microseconds) ...
   vq_fallback_rows_kernel<<<4 * sm_count(), FB_THREADS, smem, s>>>(
       a.z, a.ws.et, a.ws.e2, a.embed, a.D, a.H, a.W, a.K, Kpad, a.ws.fb_rows, a.ws.misc, a.ids, a.ids_nat, a.q,
-      a.ws.loss_acc, a.stats ? a.ws.counts : nullptr, sums);
+      a.ws.loss_acc, a.stats ? a.ws.counts : nullptr, sums, ids_mode_of(a.flags));
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   // ... long lists (degenerate codebooks): the tiled fp32 search over the listed rows; exits at once otherwise
   vq_assign_simt_kernel<<<2 * sm_count(), 256, 0, s>>>(a.z, a.ws.et, a.ws.e2, a.embed, a.B, a.D, a.H, a.W, a.K, Kpad,
                                                       a.ws.fb_rows, a.ws.misc, a.ids, a.ids_nat, a.q, a.ws.loss_acc,
-                                                      a.stats ? a.ws.counts : nullptr, sums);
+                                                      a.stats ? a.ws.counts : nullptr, sums, ids_mode_of(a.flags));
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
   return VQ_OK;

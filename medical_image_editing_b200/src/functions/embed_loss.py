@@ -28,7 +28,16 @@ def _stream() -> int:
 
 
 def labels_from_onehot(r_ids: torch.Tensor) -> torch.Tensor:
-    """(b, n_clusters, h, w) one-hot (rows of zeros = no class) -> int32 (b, h, w), 0 = no class, k + 1 = class k."""
+    """(b, n_clusters, h, w) one-hot (rows of zeros = no class) -> int32 (b, h, w), 0 = no class, k + 1 = class k.
+    Only HARD one-hot maps are supported (what `OneHotEncoder` produces, single_window_trainer.py:91-99): the reference
+    multiplies by `r_ids`, so a soft / weighted map would weight the distances -- that is rejected here, not approximated
+    (set VQ_B200_CHECK_IDS=0 to skip the check and its device synchronisation)."""
+    import os
+    if os.environ.get("VQ_B200_CHECK_IDS", "1") != "0":
+        hard = ((r_ids == 0) | (r_ids == 1)).all() & (r_ids.sum(1) <= 1).all()
+        if not bool(hard):
+            raise ValueError("B200 EmbeddingLoss: r_ids must be a hard one-hot map (values in {0, 1}, at most one class per "
+                             "pixel) or an integer label map; soft / weighted maps are not supported")
     present = r_ids.sum(1) > 0
     return ((r_ids.argmax(1) + 1) * present).to(torch.int32)
 
@@ -42,19 +51,28 @@ class _CrossLoss(torch.autograd.Function):
             raise RuntimeError("B200 EmbeddingLoss: tensors must be CUDA tensors; there is no CPU fallback")
         if z.dtype != torch.float32 or embed.dtype != torch.float32:
             raise TypeError("B200 EmbeddingLoss: embed / codebook must be float32 (the reference runs fp32)")
+        if z.dim() != 4:
+            raise ValueError(f"B200 EmbeddingLoss: embed must be [B, D, H, W], got {tuple(z.shape)}")
         B, D, H, W = z.shape
         K = embed.shape[0]
-        z = z.contiguous()
-        labels = labels.to(torch.int32).contiguous()
-        embed = embed.contiguous()
-        L = lib()
-        wb = int(L.vq_embed_loss_work_bytes(B, K))
-        work = torch.empty(wb + 256, dtype=torch.uint8, device=z.device)
-        off = (-work.data_ptr()) % 256
-        weights = torch.empty(B * K, dtype=torch.float32, device=z.device)
-        loss = torch.empty((), dtype=torch.float32, device=z.device)
-        check(L.vq_embed_loss_fwd(z.data_ptr(), labels.data_ptr(), embed.data_ptr(), B, D, H, W, K, loss.data_ptr(),
-                                  weights.data_ptr(), work.data_ptr() + off, wb, _stream()), "vq_embed_loss_fwd")
+        if tuple(labels.shape) != (B, H, W):             # a mismatch would read out of bounds in the kernel
+            raise ValueError(f"B200 EmbeddingLoss: label map must be {(B, H, W)} for embed {tuple(z.shape)}, got {tuple(labels.shape)}")
+        if embed.dim() != 2 or embed.shape[1] != D:
+            raise ValueError(f"B200 EmbeddingLoss: codebook must be (n_features={D}, n_clusters), got {tuple(embed.t().shape)}")
+        if labels.device != z.device or embed.device != z.device:
+            raise RuntimeError("B200 EmbeddingLoss: embed, labels and codebook must be on the same device")
+        with torch.cuda.device(z.device):                # launch on z's device and ITS current stream
+            z = z.contiguous()
+            labels = labels.to(torch.int32).contiguous()
+            embed = embed.contiguous()
+            L = lib()
+            wb = int(L.vq_embed_loss_work_bytes(B, K))
+            work = torch.empty(wb + 256, dtype=torch.uint8, device=z.device)
+            off = (-work.data_ptr()) % 256
+            weights = torch.empty(B * K, dtype=torch.float32, device=z.device)
+            loss = torch.empty((), dtype=torch.float32, device=z.device)
+            check(L.vq_embed_loss_fwd(z.data_ptr(), labels.data_ptr(), embed.data_ptr(), B, D, H, W, K, loss.data_ptr(),
+                                      weights.data_ptr(), work.data_ptr() + off, wb, _stream()), "vq_embed_loss_fwd")
         ctx.save_for_backward(z, labels, embed, weights)
         return loss
 
@@ -64,10 +82,11 @@ class _CrossLoss(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return None, None, None
         B, D, H, W = z.shape
-        g = g_loss.to(torch.float32).contiguous()
-        g_z = torch.empty_like(z)
-        check(lib().vq_embed_loss_bwd(g.data_ptr(), z.data_ptr(), labels.data_ptr(), embed.data_ptr(),
-                                      weights.data_ptr(), g_z.data_ptr(), B, D, H, W, embed.shape[0], _stream()), "vq_embed_loss_bwd")
+        with torch.cuda.device(z.device):
+            g = g_loss.to(torch.float32).contiguous()
+            g_z = torch.empty_like(z)
+            check(lib().vq_embed_loss_bwd(g.data_ptr(), z.data_ptr(), labels.data_ptr(), embed.data_ptr(),
+                                          weights.data_ptr(), g_z.data_ptr(), B, D, H, W, embed.shape[0], _stream()), "vq_embed_loss_bwd")
         return g_z, None, None
 
 

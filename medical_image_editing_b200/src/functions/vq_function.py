@@ -191,8 +191,9 @@ class VQFunction(torch.autograd.Function):
         K = embed.shape[0]
         if embed.shape[1] != D:
             raise ValueError(f"B200 VQ: input has {D} channels but the codebook has emb_dim={embed.shape[1]}")
-        if H != W:
+        if H != W and not (int(flags) & 16):
             # the reference views a (b,w,h)-ordered flatten as (b,h,w) (vq_module.py:171,178): square only
+            # (the natural-order code map, VQ_FLAG_IDS_NATURAL, has no such restriction)
             raise ValueError(f"B200 VQ: only square feature maps are supported (got H={H}, W={W})")
         if reduce_mode not in REDUCE_MODES:
             raise ValueError(f"reduce_mode must be one of {REDUCE_MODES}, got {reduce_mode!r}")

@@ -33,7 +33,8 @@ class VQModule(nn.Module):
     enqueues next; every access through this module (`forward`, `lookup`, `get_codebook`, `state_dict`) joins the
     streams first.  Read the buffer attributes directly only after `sync_codebook()`.  `accumulate_steps=n` sums the
     EMA statistics of n training forwards (micro-batches) and applies them in one exchange + one update after the n-th
-    (== one forward on the concatenated batch); `flush_ema()` applies a partial accumulation."""
+    (== one forward on the concatenated batch); `flush_ema()` applies a partial accumulation.  `ids_layout="natural"`
+    and `ids_base=1` return the code map as the callers build it next (transposed back to (b, h, w), 1-based)."""
 
     def __init__(self,
                  emb_dim: int,
@@ -44,6 +45,8 @@ class VQModule(nn.Module):
                  reduce_mode: str = "reference",
                  overlap_exchange: bool = False,
                  accumulate_steps: int = 1,
+                 ids_layout: str = "reference",
+                 ids_base: int = 0,
                  ) -> None:
         super().__init__()
         if reduce_mode not in REDUCE_MODES:
@@ -55,6 +58,13 @@ class VQModule(nn.Module):
         self._knn_backend = knn_backend
         self.reduce_mode = reduce_mode
         self.overlap_exchange = overlap_exchange
+        if ids_layout not in ("reference", "natural") or ids_base not in (0, 1):
+            raise ValueError("ids_layout must be 'reference' or 'natural', ids_base 0 or 1")
+        # `ids` as the callers want it next: every reference network does `ids = transpose(ids, 1, 2); ids += 1` right
+        # after the call (vqwnet.py:110-111, unet_encoder.py:115-116, vqvnet.py:62-63) -- two passes over an N-element
+        # int64 map.  ids_layout="natural" / ids_base=1 write that form straight from the search epilogue.
+        self.ids_layout = ids_layout
+        self.ids_base = ids_base
         self.kernel_flags = 0
         # micro-batching (BASELINE config 5 at 2 / 4 GPUs): the EMA statistics of `accumulate_steps` training forwards
         # are summed and applied in ONE exchange + update after the last one == one forward on the concatenated batch
@@ -89,8 +99,9 @@ class VQModule(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def forward(self, input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        flags = self.kernel_flags | (16 if self.ids_layout == "natural" else 0) | (32 if self.ids_base == 1 else 0)
         return VQFunction.apply(input, self.embed, self.cluster_size, self.embed_avg,
-                                self.momentum, self.eps, self.training, self.reduce_mode, self.kernel_flags,
+                                self.momentum, self.eps, self.training, self.reduce_mode, flags,
                                 self.overlap_exchange, self._accumulator)
 
     @property

@@ -77,6 +77,7 @@ class GradientBuckets:
         self.params = [p for p in params if p.requires_grad]
         self.buckets, self._pending, self._works, self._handles = [], [], [], []
         self._of = {}
+        self.defer = False            # micro-batching: gradients of all but the last micro-batch only accumulate
         if self.ws == 1 or not self.params:
             return
         cur, cur_bytes = [], 0
@@ -115,7 +116,14 @@ class GradientBuckets:
                 off += p.numel()
         self._works = []
 
+    def rearm(self) -> None:
+        """Next micro-batch of the same step: keep the accumulated gradients, count the hooks again."""
+        for bi, (_, ps) in enumerate(self.buckets):
+            self._pending[bi] = len(ps)
+
     def _ready(self, p) -> None:
+        if self.defer:
+            return
         bi = self._of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -167,16 +175,33 @@ class DataParallelVQTrainer:
         self.world_size = _world(group)
         self.buckets = GradientBuckets(self.params, group)
 
-    def training_step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def training_step(self, images: torch.Tensor, micro_batches: int = 1) -> Dict[str, torch.Tensor]:
+        """One optimiser step on THIS RANK's shard.  `micro_batches > 1` (BASELINE config 5 at 2 / 4 GPUs: 64 / 32 slices
+        of 512 x 512 per GPU do not fit one forward) splits the shard, accumulates the gradients and -- through the
+        quantisers' `accumulate_steps` -- the EMA statistics, and exchanges both once: the step equals the one-shot step
+        on the whole shard (up to fp32 summation order)."""
         self.model.train(True)
         if self.world_size > 1:
             self.buckets.zero()
         else:
             self.optimizer.zero_grad(set_to_none=True)
-        out = self.model(images)
-        recon_loss = F.mse_loss(out["recon"], images)
-        loss = recon_loss + self.commit_weight * out["commit_loss"]
-        loss.backward()                                   # bucket all-reduces are launched from inside the backward
+        n = max(1, int(micro_batches))
+        if images.shape[0] % n:
+            raise ValueError(f"batch of {images.shape[0]} slices does not split into {n} equal micro-batches")
+        for mod in self.model.modules():
+            if hasattr(mod, "accumulate_steps") and hasattr(mod, "embed_avg") and mod.accumulate_steps != n:
+                mod.accumulate_steps = n
+        mb = images.shape[0] // n
+        out, loss, recon_loss = None, None, None
+        for i in range(n):
+            x = images[i * mb:(i + 1) * mb]
+            out = self.model(x)
+            recon_loss = F.mse_loss(out["recon"], x)
+            loss = recon_loss + self.commit_weight * out["commit_loss"]
+            self.buckets.defer = i < n - 1                # only the last micro-batch's backward launches the exchange
+            if i == n - 1:
+                self.buckets.rearm()
+            (loss / n if n > 1 else loss).backward()      # bucket all-reduces are launched from inside the backward
         self.buckets.finish()
         self.optimizer.step()
         return {"loss": loss.detach(), "recon_loss": recon_loss.detach(), "commit_loss": out["commit_loss"].detach(),

@@ -172,3 +172,46 @@ def test_trainer_two_ranks_equal_single_process_on_concatenated_batch():
         tr.training_step(x)
     for a, p in zip(ret[0]["params"], model.parameters()):
         assert np.allclose(a, p.detach().numpy(), rtol=1e-4, atol=1e-6)
+
+
+def _trainer_micro_worker(rank, ws, port, ret):
+    import torch.distributed as dist
+    os.environ.update(WORLD_SIZE=str(ws), RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from medical_image_editing_b200.src.trainers import DataParallelVQTrainer
+    torch.manual_seed(100 + rank)
+    model = _ToyModel()
+    tr = DataParallelVQTrainer(model, lr=1e-2, commit_weight=0.5)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 1, 8, 8, generator=g)
+    for _ in range(3):
+        tr.training_step(x[rank * 4:(rank + 1) * 4], micro_batches=2)      # 2 ranks x 2 micro-batches of 2 slices
+    ret[rank] = dict(params=[p.detach().numpy().copy() for p in model.parameters()], end_sync=tr.replicas_in_sync())
+    dist.destroy_process_group()
+
+
+def test_trainer_micro_batches_equal_one_shot_step():
+    """BASELINE config 5 at 2 / 4 GPUs: the shard is processed in micro-batches, gradients accumulate in the buckets
+    and are exchanged once -- same parameters as one process on the whole batch."""
+    ret = _spawn(_trainer_micro_worker, 29759)
+    assert ret[0]["end_sync"] and ret[1]["end_sync"]
+    for a, b in zip(ret[0]["params"], ret[1]["params"]):
+        assert np.array_equal(a, b)
+    from medical_image_editing_b200.src.trainers import DataParallelVQTrainer
+    torch.manual_seed(100)
+    model = _ToyModel()
+    tr = DataParallelVQTrainer(model, lr=1e-2, commit_weight=0.5)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 1, 8, 8, generator=g)
+    for _ in range(3):
+        tr.training_step(x)
+    for a, p in zip(ret[0]["params"], model.parameters()):
+        assert np.allclose(a, p.detach().numpy(), rtol=1e-4, atol=1e-6)
+    # single process, micro-batched: also the same
+    torch.manual_seed(100)
+    model2 = _ToyModel()
+    tr2 = DataParallelVQTrainer(model2, lr=1e-2, commit_weight=0.5)
+    for _ in range(3):
+        tr2.training_step(x, micro_batches=4)
+    for p2, p in zip(model2.parameters(), model.parameters()):
+        assert np.allclose(p2.detach().numpy(), p.detach().numpy(), rtol=1e-4, atol=1e-6)

@@ -640,6 +640,42 @@ def test_micro_batch_accumulation_equals_one_big_batch(n_micro, flags):
     assert not m.flush_ema()
 
 
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("K,D,H", [(512, 64, 32), (10, 16, 64), (64, 256, 16), (100, 24, 8)])
+def test_natural_one_based_ids_from_the_epilogue(K, D, H, flags):
+    """`ids_layout="natural", ids_base=1` == the reference module followed by what every caller does
+    next, `ids = transpose(ids, 1, 2); ids += 1` (vqwnet.py:110-111, unet_encoder.py:115-116) -- all search kernels."""
+    B = 3
+    z, embed = seeded_case(B, D, H, H, K, seed=77 + K)
+    ora = make_oracle(K, D, embed)
+    ora.eval()
+    with torch.no_grad():
+        _, _, ids_ref = ora(z)
+    want = torch.transpose(ids_ref, 1, 2) + 1
+    for training in (False, True):
+        m = new_vq(K, D, 0.99, flags, ids_layout="natural", ids_base=1)
+        set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+        m.train(training)
+        zz = z.to(DEV).requires_grad_(True)
+        q, loss, ids = m(zz)
+        (g,) = torch.autograd.grad(q.sum() + loss, zz)        # the backward keeps using the 0-based natural map
+        assert ids.dtype == torch.int64 and ids.shape == (B, H, H)
+        assert torch.equal(ids.cpu(), want)
+        assert torch.equal(q.detach().cpu(), F.embedding(ids_ref, ora.embed).transpose(1, -1).contiguous())
+        assert torch.isfinite(g).all()
+    # natural order lifts the reference's square-only restriction
+    zr = torch.randn(2, D, 8, 16, generator=torch.Generator().manual_seed(5))
+    m = new_vq(K, D, 0.99, flags, ids_layout="natural")
+    set_state(m, ora.embed.numpy(), ora.cluster_size.numpy(), ora.embed_avg.numpy())
+    m.eval()
+    with torch.no_grad():
+        _, _, ids = m(zr.to(DEV))
+        flat = zr.permute(0, 2, 3, 1).reshape(-1, D)
+        from oracle.vq_oracle import torch_knn_l2
+        _, ids_flat = torch_knn_l2(ora.embed, flat)
+    assert torch.equal(ids.cpu().reshape(-1), ids_flat.reshape(-1))
+
+
 def test_embed_avg_layouts():
     """`embed.T.clone()` (vq_module.py:156) keeps strides (1, D); a checkpoint round trip can make the
     buffer contiguous.  Both must give the reference's update."""
