@@ -716,8 +716,25 @@ vq_lookup_nchw_t_kernel(const int64_t* __restrict__ ids, const float* __restrict
       const float* e3 = E + (size_t)(i3 < 0 ? 0 : i3) * D;
       float* o = out + (((long long)b * D) * C + c) * A + a;
       const long long dstride = (long long)C * A;
+      int d = 0;
+      if ((D & 3) == 0 && ((((uintptr_t)E) & 15) == 0)) {
+        // four channels at a time: one 16-byte load per code row (the codebook sits in L1), a 4 x 4 transpose in
+        // registers, four 16-byte streaming stores -- 2.5 x fewer load/store instructions than a scalar gather
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (; d + 4 <= D; d += 4) {
+          const float4 r0 = i0 < 0 ? zero : __ldg(reinterpret_cast<const float4*>(e0 + d));
+          const float4 r1 = i1 < 0 ? zero : __ldg(reinterpret_cast<const float4*>(e1 + d));
+          const float4 r2 = i2 < 0 ? zero : __ldg(reinterpret_cast<const float4*>(e2 + d));
+          const float4 r3 = i3 < 0 ? zero : __ldg(reinterpret_cast<const float4*>(e3 + d));
+          __stcs(reinterpret_cast<float4*>(o + (d + 0) * dstride), make_float4(r0.x, r1.x, r2.x, r3.x));
+          __stcs(reinterpret_cast<float4*>(o + (d + 1) * dstride), make_float4(r0.y, r1.y, r2.y, r3.y));
+          __stcs(reinterpret_cast<float4*>(o + (d + 2) * dstride), make_float4(r0.z, r1.z, r2.z, r3.z));
+          __stcs(reinterpret_cast<float4*>(o + (d + 3) * dstride), make_float4(r0.w, r1.w, r2.w, r3.w));
+        }
+      }
 #pragma unroll 4
-      for (int d = 0; d < D; ++d) {
+      for (; d < D; ++d) {
         float4 v;
         v.x = i0 < 0 ? 0.f : __ldg(e0 + d);
         v.y = i1 < 0 ? 0.f : __ldg(e1 + d);
