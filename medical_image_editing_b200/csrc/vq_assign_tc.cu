@@ -2010,6 +2010,37 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs a microsecond or two of host time and a forward builds up to four maps: the maps of
+// the last calls are kept (per host thread), keyed on everything that goes into them -- a training loop that reuses its
+// buffers (or replays the caching allocator's blocks) encodes nothing after the first steps.
+static CUresult encode_cached(EncodeTiledFn enc, CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* ptr,
+                              const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                              const cuuint32_t* es, CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                              CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+  struct Key {
+    void* ptr; int dev; uint32_t rank, sw, l2;
+    uint64_t dims[3], strides[2];
+    uint32_t box[3];
+  };
+  struct Entry { Key k; CUtensorMap m; bool used; };
+  constexpr int N = 16;
+  static thread_local Entry cache[N];
+  static thread_local int next = 0;
+  Key k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr; k.dev = current_device(); k.rank = rank; k.sw = (uint32_t)sw; k.l2 = (uint32_t)l2;
+  for (cuuint32_t i = 0; i < rank && i < 3; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (cuuint32_t i = 0; i + 1 < rank && i < 2; ++i) k.strides[i] = strides[i];
+  for (int i = 0; i < N; ++i)
+    if (cache[i].used && memcmp(&cache[i].k, &k, sizeof(k)) == 0) { *out = cache[i].m; return CUDA_SUCCESS; }
+  const CUresult r = enc(out, dt, rank, ptr, dims, strides, box, es, il, sw, l2, oob);
+  if (r == CUDA_SUCCESS) {
+    cache[next].k = k; cache[next].m = *out; cache[next].used = true;
+    next = (next + 1) % N;
+  }
+  return r;
+}
+
 static int sm_count_tc() { return device_sm_count(); }
 
 static bool tcs_supported(int D, int K) { return tcs_geometry(D, K).ok; }
@@ -2036,7 +2067,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
     cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
     cuuint32_t box[3] = {32, TC_DCH, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.q, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.q, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(q) failed: %d", (int)r);
@@ -2048,7 +2079,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
     cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
     cuuint32_t box[3] = {32, TC_DCH, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
@@ -2058,7 +2089,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
     cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
     cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
@@ -2149,7 +2180,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
     cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
     cuuint32_t box[3] = {32, TC_DCH, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
@@ -2159,7 +2190,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
     cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
     cuuint32_t box[2] = {TC_DCH, (cuuint32_t)(pair ? g.BN / 2 : g.BN)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
@@ -2170,7 +2201,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
     cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
     cuuint32_t box[3] = {16, TC_DCH, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.q, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &qmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.q, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(q) failed: %d", (int)r);
@@ -2183,7 +2214,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
     cuuint64_t strides[1] = {256};
     cuuint32_t box[2] = {64, (cuuint32_t)(pair ? g.BN / 16 : g.BN / 8)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)eaug_img, dims, strides, box, es,
+    CUresult r = encode_cached(enc, &amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)eaug_img, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(augmentation) failed: %d", (int)r);

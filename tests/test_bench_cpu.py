@@ -1,11 +1,15 @@
-"""CPU: the reference arm of bench.py (the CPU port of the reference's op chain) prints its JSON line, also when it is
-launched the way the driver launches the N > 1 arms (torchrun sets WORLD_SIZE / RANK; ranks > 0 exit without work)."""
+"""CPU: the reference arm of bench.py (the reference's own module when a copy of the reference is reachable, else the
+CPU port of its op chain) prints its JSON line, also when it is launched the way the driver launches the N > 1 arms
+(torchrun sets WORLD_SIZE / RANK; ranks > 0 exit without work)."""
 import json
 import os
 import subprocess
 import sys
 
 from util import ROOT
+from oracle import ref_loader
+
+KIND = "reference" if ref_loader.reference_available() else "port"
 
 
 def _run(env_extra):
@@ -20,7 +24,7 @@ def _run(env_extra):
 def test_reference_arm_single_process():
     d = json.loads(_run({}).splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "vq_lookups_per_s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == KIND and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_reference_arm_under_torchrun_env():
@@ -38,4 +42,17 @@ def test_reference_arm_vqwnet_workload():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "vqwnet_train_slices_per_s" and d["unit"] == "slices/s"
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == KIND and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_falls_back_to_the_port_without_a_reference_copy():
+    """With no copy of the reference reachable ($VQ_REF_SRC pointing nowhere does not help: the loader also looks at
+    /root/reference and the mirror), the port must still print the line: force it by hiding both locations."""
+    code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','1'];"
+            "from oracle import ref_loader; ref_loader.REF_SRC_CANDIDATES[:] = ['/nonexistent'];"
+            "import runpy; runpy.run_path('bench.py', run_name='__main__')")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=600,
+                       env=dict(os.environ, VQ_REF_BUDGET_S="5"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0

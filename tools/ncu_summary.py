@@ -82,7 +82,10 @@ def main():
                 if not parts:
                     continue
                 op = parts[1] if parts[0].startswith("@") and len(parts) > 1 else parts[0]
-                n = int(r[ix["Instructions Executed"]] or 0)
+                try:
+                    n = int(r[ix["Instructions Executed"]] or 0)
+                except ValueError:          # the header row of the next profiled launch: only the first one is summarised
+                    break
                 ops[op.split(".")[0]] += n
                 tot += n
                 for c in stall_cols:
