@@ -955,7 +955,8 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 #pragma unroll
             for (int t = 0; t < NZQ; ++t) {
               const uint32_t j = (uint32_t)(2 * t) + (uint32_t)hf;
-              const float4 e4 = lds_v4(eb + (uint32_t)((2 * t) >> 3) * bn128 + (((j & 7) << 4) ^ r7));
+              float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (act) e4 = lds_v4(eb + (uint32_t)((2 * t) >> 3) * bn128 + (((j & 7) << 4) ^ r7));    // idle lanes load nothing
               dot = __fmaf_rn(zq[t][0], e4.x, dot);
               dot = __fmaf_rn(zq[t][1], e4.y, dot);
               dot = __fmaf_rn(zq[t][2], e4.z, dot);
@@ -1069,6 +1070,961 @@ vq_assign_tc_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// resident kernel, third generation (emb_dim = 64): decoupled roles, LSU-lean epilogue
+// ---------------------------------------------------------------------------------------------
+// The kernel above is bound by the shared-memory / LSU data pipe (ncu: 82 % of the wavefront peak in training mode,
+// 60 % in eval; profiles/r02b_*): conflicted 4-byte z copies, code rows re-read by every re-rank pass of every lane, q
+// leaving in 64-byte runs, and one long serial chain per tile in the output warps.  This kernel keeps the search
+// (tcgen05 tf32 scores in TMEM, rigorous bound, exact fp32 re-rank, exhaustive fallback list) and reorganises the rest:
+//   warp 11      TMA producer (as above)                       warp 15  MMA issuer (as above)
+//   warp 18      |z|^2: lane = 4 adjacent pixels (16-byte shared-memory loads, conflict-free)
+//   warps 0..7   scan: thread = (pixel, column group).  16 accumulator columns per tcgen05.ld, the next load in flight while
+//                the current one is reduced; every column enters two max-reductions over orthogonal partitions of the
+//                thread's columns -- quarter-chunks (8 consecutive columns) and residues (column index mod 8) -- so a
+//                column can only be a candidate if its quarter AND its residue are hot: one instruction per score, no
+//                per-column mask.  Bounds + records go to the `pub` slot.
+//   8 output warps (8-10, 12-14, 16, 17): two software-pipelined jobs per iteration j:
+//                merge(j)      thread = pixel (output warps 0..3 / 4..7 take the even / odd tiles): the two column groups'
+//                              records -> one candidate cell: winner into the `win` ring (+ code map, histogram); several:
+//                              the pixel goes to the straggler queue and its z row is gathered into the queue entry with
+//                              cp.async (nobody waits for that load); overflow / non-finite / exploded-code doubt:
+//                              fallback list
+//                outputs(j-2)  thread = (4 adjacent pixels, 2 channel quads).  z: 16-byte global loads (L2 hits: the TMA
+//                              has just brought the tile in), so the shared-memory stage is held only by the tensor core
+//                              and the |z|^2 warp; code rows: two 16-byte loads per pixel; q: 16-byte stores, a quarter-warp
+//                              writes one full 128-byte line; (z-q)^2; EMA sums (red.v4, 64 contiguous bytes per pixel and
+//                              instruction, equal codes among the four pixels summed first)
+//   warp 19      stragglers: exact fp32 re-rank (the library's two-chain dot product, two lanes per pixel, two candidate
+//                cells per pass) of the queued pixels from the z rows in the queue; writes the winner into the `win` ring
+// The output job waits for a tile's `win` slot to be complete (128 arrivals: decided pixels by the merging warps, the
+// rest by the straggler warp), two tiles behind the merge: q / loss / sums have a single writer, no ordering between roles
+// is needed, and the straggler warp has two tile periods per batch.
+constexpr int R3_D = 64;
+constexpr int R3_ND = R3_D / TC_DCH;                 // 2 chunks of 32 channels
+constexpr int R3_SCAN_WARPS = 8, R3_OUT_WARPS = 8;
+constexpr int R3_WARPS = TC_AUX_WARPS + R3_SCAN_WARPS + R3_OUT_WARPS;      // 20 warps: five per scheduler, 96 registers per thread
+constexpr int R3_THREADS = 32 * R3_WARPS;
+// warp -> role.  Scan warp w (0..7) reads TMEM lane quadrant w & 3.  A scheduler (warp id mod 4) shares its issue slots
+// evenly among its ready warps, so a serial role runs at the pace of its scheduler's crowd: the straggler warp shares
+// scheduler 3 with the two light single-thread roles (TMA producer, MMA issuer) instead of two output warps
+//   scheduler 0: scan 0, 4, output 8, 12, 16      scheduler 1: scan 1, 5, output 9, 13, 17
+//   scheduler 2: scan 2, 6, output 10, 14, |z|^2 18      scheduler 3: scan 3, 7, producer 11, MMA 15, stragglers 19
+constexpr int R3_W_PROD = 11, R3_W_MMA = 15, R3_W_ZN = 18, R3_W_STRAG = 19;
+// output warp index (0..7) of a hardware warp, or -1
+__device__ __forceinline__ int r3_out_index(int warp) {
+  switch (warp) {
+    case 8: return 0; case 9: return 1; case 10: return 2; case 12: return 3;
+    case 13: return 4; case 14: return 5; case 16: return 6; case 17: return 7;
+    default: return -1;
+  }
+}
+constexpr int R3_ZSTAGE = R3_ND * TC_TILE * 128;     // 32 KB
+constexpr int R3_QCAP = 16;                          // straggler queue entries: deferral rate x (gather latency + batch time), with margin
+constexpr int R3_LAG = 3;                            // the output job runs this many tiles behind the merge
+constexpr int R3_QSTRIDE = 272;                      // bytes per entry: z row (256) + four records; 68 floats: conflict-free 16-byte reads
+constexpr int R3_WINS = 4;                           // win ring slots (outputs run two tiles behind the merge)
+constexpr int R3_MAXCAND = 16;                       // candidate cells re-scored exactly per pixel (more: fallback list)
+constexpr uint32_t R3_WIN_SKIP = 0x80000000u;        // `win` entry of a pixel on the fallback list
+
+struct R3Geom {
+  int BN, nb;
+  size_t off_emain, off_eaug, off_aaug, off_z, off_pub, off_win, off_zn, off_hist, off_perm, off_ctab, off_queue, off_bar, total;
+  bool ok;
+};
+
+static R3Geom r3_geometry(int K) {
+  R3Geom g{};
+  g.ok = false;
+  g.BN = 32;
+  while (g.BN < K && g.BN < TC_MAXBN) g.BN <<= 1;
+  g.nb = (K + g.BN - 1) / g.BN;
+  if (g.nb > 2) return g;                       // 512 TMEM columns = two accumulator blocks
+  const size_t ktot = (size_t)g.nb * g.BN;
+  size_t off = 0;
+  g.off_emain = off; off += ktot * R3_ND * 128;
+  g.off_eaug = off;  off += align_up(ktot * 32, 1024);
+  g.off_aaug = off;  off += 4096;
+  g.off_z = off;     off += 2 * (size_t)R3_ZSTAGE;
+  g.off_pub = off;   off += 2 * TC_TILE * 16;            // [column group][pixel] x 16 B (one slot: the merge reads it at once)
+  g.off_win = off;   off += R3_WINS * TC_TILE * 4;       // [tile & 3][pixel]
+  g.off_zn = off;    off += 3 * TC_TILE * 4;             // [tile % 3][pixel]
+  g.off_hist = off;  off += align_up((size_t)((K + 1) / 2) * 4, 16);      // two 16-bit counters per word (a CTA sees < 65536 pixels: checked at launch)
+  g.off_perm = off;  off += align_up(ktot * 2, 16);
+  g.off_ctab = off;  off += align_up((size_t)g.nb * (g.BN / 32) * 8, 16);
+  g.off_queue = off; off += R3_QCAP * R3_QSTRIDE + 24 * 8 + 96 + 32 + 16 * 8 + 16 * 4;   // entries, entry barriers, {iteration << 7 | pixel}, {tail, head, warps done}
+  g.off_bar = off;   off += 256;
+  g.total = off;            // no slack: the kernel checks that the dynamic shared memory starts 1024-byte aligned
+  g.ok = g.total <= (size_t)TC_SMEM_LIMIT;
+  return g;
+}
+
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+#ifndef VQ_R3_RELAXED_SLEEP
+#define VQ_R3_RELAXED_SLEEP 0
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (VQ_R3_RELAXED_SLEEP) mbar_wait_sleep(bar, parity, VQ_R3_RELAXED_SLEEP);
+  else mbar_wait(bar, parity);      // try_wait with a suspend-time hint: the hardware parks the warp on the barrier
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0u;
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {      // arrives on `bar` once this thread's copies have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_s32(int* p, int v) {
+  asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that the compiler cannot move the uses of `r` across (the registers are in/out operands)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// Scan state of one thread (pixel, column group), accumulator units a_k = z.e_k - |e_k|^2/2:
+//   L     lower bound on the best exact a_k among the columns seen so far = max_c (chunkmax_c - delta_c)
+//   Urec  upper bound on the exact a_k of every recorded candidate
+//   recA / recB  records of the (at most two) blocks with hot columns: block << 24 | hot quarter-chunks << 8 | hot residues
+//                (bit 15-q of the quarter field: quarter q of the thread's columns in that block; bit 7-j: residue j);
+//                cnt > 2: overflow (fallback list)
+struct R3Scan {
+  float L, Urec;
+  int cnt;
+  uint32_t recA, recB;
+};
+
+// 16 columns (half a chunk): two quarter maxima and the eight residue maxima, 16 three-input max instructions
+__device__ __forceinline__ void r3_reduce16(const uint32_t (&b)[16], float& q0, float& q1, float (&R)[8]) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(b[j]);
+  q0 = fmaxf(fmax3(fmax3(v[0], v[1], v[2]), fmax3(v[3], v[4], v[5]), v[6]), v[7]);
+  q1 = fmaxf(fmax3(fmax3(v[8], v[9], v[10]), fmax3(v[11], v[12], v[13]), v[14]), v[15]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) R[j] = fmax3(R[j], v[j], v[j + 8]);
+}
+
+// all columns of one accumulator block that belong to this thread: chunks cg, cg + 2, ... (32 columns each), read as
+// half-chunks with the next tcgen05.ld in flight.  hm[2 i + h]: quarter maxima of half-chunk i, R: residue maxima
+__device__ __forceinline__ void r3_block_maxima(uint32_t taddr, int cg, int nchunks, float (&hm)[16], float (&R)[8]) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) hm[q] = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) R[j] = -INFINITY;
+  uint32_t b0[16], b1[16];
+  if (nchunks == 8) {                                   // (warp-uniform) 256-code block: four chunks per thread, no guards
+    const uint32_t t0 = taddr + (uint32_t)(32 * cg);
+    tmem_ld16(t0, b0);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      tmem_ld_wait16(b0);
+      tmem_ld16(t0 + (uint32_t)(64 * (i >> 1) + 16), b1);
+      r3_reduce16(b0, hm[2 * i], hm[2 * i + 1], R);
+      tmem_ld_wait16(b1);
+      if (i + 2 < 8) tmem_ld16(t0 + (uint32_t)(64 * ((i + 2) >> 1)), b0);
+      r3_reduce16(b1, hm[2 * i + 2], hm[2 * i + 3], R);
+    }
+    return;
+  }
+  const int nmine = (nchunks - cg + 1) >> 1;            // chunks of this thread (warp-uniform), <= 4
+  const int nh = 2 * nmine;                             // half-chunks
+  // half-chunk i: chunk cg + 2 (i >> 1), half i & 1 -> first column 32 cg + 64 (i >> 1) + 16 (i & 1)
+  tmem_ld16(taddr + (uint32_t)(32 * cg), b0);
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    if (i < nh) {
+      tmem_ld_wait16(b0);
+      tmem_ld16(taddr + (uint32_t)(32 * cg + 64 * (i >> 1) + 16), b1);
+      r3_reduce16(b0, hm[2 * i], hm[2 * i + 1], R);
+      tmem_ld_wait16(b1);
+      if (i + 2 < nh) tmem_ld16(taddr + (uint32_t)(32 * cg + 64 * ((i + 2) >> 1)), b0);
+      r3_reduce16(b1, hm[2 * i + 2], hm[2 * i + 3], R);
+    }
+  }
+}
+
+// end of a block: bounds, hot quarters, hot residues, record
+__device__ __forceinline__ void r3_block_end(R3Scan& st, const float (&hm)[16], const float (&R)[8], int cg, int nchunks,
+                                             int blk, uint32_t ctab_s, float zn) {
+  float dl[4];
+  float bm = -INFINITY, dmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = cg + 2 * i;
+    dl[i] = 0.f;
+    if (c < nchunks) {                                    // warp-uniform
+      const float2 ab = lds_v2(ctab_s + (uint32_t)(blk * nchunks + c) * 8);
+      dl[i] = __fmaf_rn(zn, ab.x, ab.y);
+      const float m = fmaxf(fmaxf(hm[4 * i], hm[4 * i + 1]), fmaxf(hm[4 * i + 2], hm[4 * i + 3]));
+      st.L = fmaxf(st.L, m - dl[i]);
+      bm = fmaxf(bm, m);
+      dmax = fmaxf(dmax, dl[i]);
+    }
+  }
+  if (st.Urec < st.L) { st.cnt = 0; st.Urec = -INFINITY; }           // nothing recorded so far can still win
+  // "below threshold" sign bits, gathered by short independent funnel-shift chains (one per chunk / residue half)
+  uint32_t nq4[4], nr2[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float T = st.L - dl[i];
+    const float2 nT2 = make_float2(-T, -T);
+    const float2 dA = __fadd2_rn(make_float2(hm[4 * i], hm[4 * i + 1]), nT2);
+    const float2 dB = __fadd2_rn(make_float2(hm[4 * i + 2], hm[4 * i + 3]), nT2);
+    uint32_t n = __float_as_uint(dA.x) >> 31;
+    n = __funnelshift_l(__float_as_uint(dA.y), n, 1);
+    n = __funnelshift_l(__float_as_uint(dB.x), n, 1);
+    nq4[i] = __funnelshift_l(__float_as_uint(dB.y), n, 1);
+  }
+  {
+    const float Tr = st.L - dmax;
+    const float2 nT2 = make_float2(-Tr, -Tr);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float2 d2 = __fadd2_rn(make_float2(R[j], R[j + 1]), nT2);
+      nr2[j >> 2] = __funnelshift_l(__float_as_uint(d2.x), nr2[j >> 2], 1);
+      nr2[j >> 2] = __funnelshift_l(__float_as_uint(d2.y), nr2[j >> 2], 1);
+    }
+  }
+  const uint32_t nq = (nq4[0] << 12) | (nq4[1] << 8) | (nq4[2] << 4) | nq4[3];
+  const uint32_t nr = (nr2[0] << 4) | nr2[1];
+  const uint32_t qm = ~nq & 0xFFFFu;                      // bit (15-q): quarter q is hot
+  const uint32_t rm = ~nr & 0xFFu;                        // bit (7-j): residue j is hot
+  const uint32_t rec = ((uint32_t)blk << 24) | (qm << 8) | rm;
+  const bool has = qm != 0u;
+  const bool s0 = has && st.cnt == 0, s1 = has && st.cnt == 1;
+  st.recA = s0 ? rec : st.recA;
+  st.recB = s1 ? rec : st.recB;
+  st.cnt += has ? 1 : 0;
+  st.Urec = has ? fmaxf(st.Urec, bm + dmax) : st.Urec;
+}
+// number of candidate cells of a record
+__device__ __forceinline__ int r3_cells(uint32_t rec) { return __popc(rec & 0x00FFFF00u) * __popc(rec & 0xFFu); }
+// sorted-codebook position of cell (quarter q, residue j) of a record of column group cg
+__device__ __forceinline__ int r3_cell_pos(uint32_t rec, int cg, int q, int j, int bnsh) {
+  return (int)((rec >> 24) << bnsh) + (cg + 2 * (q >> 2)) * 32 + (q & 3) * 8 + j;
+}
+
+// Optional event trace (build with -DVQ_R3_TRACE; read with vq_debug_tc_timing / tools/r3_trace.py): clock64 of CTA 0's first
+// 64 tiles, [event][tile]
+#ifdef VQ_R3_TRACE
+__device__ long long g_r3_trace[32 * 64];
+#define R3_EV(e, it_)                                                                                  \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && lane == 0 && (it_) < 64) g_r3_trace[(e) * 64 + (it_)] = clock64();         \
+  } while (0)
+#else
+#define R3_EV(e, it_) do { } while (0)
+#endif
+
+struct R3Params {
+  TcParams t;
+  uint32_t off_win, off_queue;
+  uint32_t zero;          // always 0 (see r3_after_loads)
+};
+// A shared-memory slot is handed back (mbarrier.arrive) right after it was read with plain loads whose values are only
+// used later.  The arrive does not wait for those loads: with the LSU queue backed up (the EMA reductions of training mode)
+// the next writer overwrote the slot before the loads had read it (measured: wrong (z-q)^2 in training mode, never in
+// eval).  Folding the loaded registers into the barrier address -- through a mask the compiler cannot see is zero --
+// makes the arrive wait on the loads' scoreboard.
+__device__ __forceinline__ uint32_t r3_after_loads(uint32_t bar, uint32_t loaded_bits, uint32_t zero) { return bar + (loaded_bits & zero); }
+
+// Debug build (-DVQ_R3_CHECK): every wait gives up after a while, records {site, tile, CTA} of the first stuck waiter in
+// misc[8..] of the workspace... (g_r3_dbg, read with vq_debug_tc_timing) and lets the kernel run to its end
+#ifdef VQ_R3_CHECK
+__device__ int g_r3_abort;
+__device__ long long g_r3_dbg[32 * 64];
+__device__ __forceinline__ void r3_dbg_wait(uint32_t bar, uint32_t parity, int site, int it) {
+  for (long long spins = 0;; ++spins) {
+    if (mbar_test(bar, parity)) return;
+    if (*(volatile int*)&g_r3_abort) return;
+    if (spins > 4000000) {
+      if (atomicExch(&g_r3_abort, 1) == 0) { g_r3_dbg[0] = site; g_r3_dbg[1] = it; g_r3_dbg[2] = blockIdx.x; g_r3_dbg[3] = threadIdx.x; }
+      const int slot = 8 + 4 * (int)(threadIdx.x >> 5);
+      if ((threadIdx.x & 31) == 0) { g_r3_dbg[slot] = site; g_r3_dbg[slot + 1] = it; g_r3_dbg[slot + 2] = blockIdx.x; }
+      return;
+    }
+    __nanosleep(20);
+  }
+}
+#define R3_WAIT(bar, par, site, it) r3_dbg_wait(bar, par, site, it)
+#define R3_WAIT_SLEEP(bar, par, ns, site, it) r3_dbg_wait(bar, par, site, it)
+#define R3_WAIT_RELAXED(bar, par, site, it) r3_dbg_wait(bar, par, site, it)
+#else
+#define R3_WAIT(bar, par, site, it) mbar_wait(bar, par)
+#define R3_WAIT_SLEEP(bar, par, ns, site, it) mbar_wait_sleep(bar, par, ns)
+#define R3_WAIT_RELAXED(bar, par, site, it) mbar_wait_relaxed(bar, par)
+#endif
+
+// next candidate cell of a queued pixel: records c[0..3] (column groups 0, 0, 1, 1), iterator (ri, qm, rm)
+struct R3Cells {
+  uint32_t c0, c1, c2, c3, cur, qm, rm;
+  int ri;
+  __device__ __forceinline__ void init(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    c0 = a; c1 = b; c2 = c; c3 = d; ri = 0; cur = a; qm = (a >> 8) & 0xFFFFu; rm = a & 0xFFu;
+  }
+  __device__ __forceinline__ int next(int bnsh) {         // precondition: a cell is left
+    while (qm == 0u || rm == 0u) {
+      ++ri;
+      cur = ri == 1 ? c1 : ri == 2 ? c2 : c3;
+      qm = (cur >> 8) & 0xFFFFu; rm = cur & 0xFFu;
+      if (ri >= 3) break;
+    }
+    const int q = __clz(qm << 16), j = __clz(rm << 24);
+    const int k = r3_cell_pos(cur, ri >> 1, q, j, bnsh);
+    rm &= ~(0x80u >> j);
+    if (rm == 0u) { qm &= ~(0x8000u >> q); rm = qm ? (cur & 0xFFu) : 0u; }
+    return k;
+  }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(R3_THREADS, 1)
+vq_assign_r3_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ CUtensorMap emap, const R3Params PP) {
+  const TcParams& P = PP.t;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();                    // swizzled TMA / UMMA tiles need 1024-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint64_t* bars = (uint64_t*)(smem + P.off_bar);
+  const uint32_t bar0 = sbase + P.off_bar;
+  // barrier slots: 0 e_full | 1,2 z_full | 3,4 z_empty | 5,6 tmem_full | 7,8 tmem_empty | 9..11 zn_full |
+  //                13..16 win_full | 17..20 win_empty | 21,22 pub_full | 24,25 pub_empty ; slot 23: tmem base
+  // (the pub slot is single, but each merging team waits on its own barrier pair: a waiter that skipped every other phase
+  // of a shared barrier would alias with the phase before -- parity waits may be at most one phase ahead)
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 23);
+  uint16_t* perm_s = (uint16_t*)(smem + P.off_perm);
+  // straggler queue: entries [R3_QCAP] x {z row, four records}, one mbarrier per entry (32 cp.async arrivals), the entries'
+  // {iteration << 7 | pixel} words, {tail, head, warps done}
+  const uint32_t queue_s = sbase + PP.off_queue;
+  const uint32_t qbar_s = queue_s + R3_QCAP * R3_QSTRIDE;
+  const uint32_t qitp_s = qbar_s + 24 * 8;
+  volatile uint32_t* qctl = (volatile uint32_t*)(smem + PP.off_queue + R3_QCAP * R3_QSTRIDE + 24 * 8 + 96);
+  const uint32_t qkey_s = qitp_s + 96 + 32;             // straggler scratch: best key per batch entry [16] x 8 B, |z|^2 per entry [16] x 4 B
+  const uint32_t qz2_s = qkey_s + 16 * 8;
+  uint32_t* hist = (uint32_t*)(smem + P.off_hist);
+  const uint32_t win_s = sbase + PP.off_win;
+
+  constexpr int nD = R3_ND;
+  const int ktot = P.nb * P.BN;
+  const int bnsh = P.bn_shift;
+  const uint32_t bn128 = (uint32_t)P.BN * 128;
+
+  if (threadIdx.x == 32) {
+    mbar_init(BAR(0), 1);
+    mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
+    mbar_init(BAR(3), 2); mbar_init(BAR(4), 2);           // the |z|^2 warp and the MMA commit
+    mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
+    mbar_init(BAR(7), R3_SCAN_WARPS); mbar_init(BAR(8), R3_SCAN_WARPS);
+    for (int i = 0; i < 3; ++i) mbar_init(BAR(9 + i), 1);
+    for (int i = 0; i < R3_WINS; ++i) { mbar_init(BAR(13 + i), TC_TILE); mbar_init(BAR(17 + i), R3_OUT_WARPS); }
+    mbar_init(BAR(21), R3_SCAN_WARPS); mbar_init(BAR(22), R3_SCAN_WARPS);
+    mbar_init(BAR(24), R3_OUT_WARPS / 2); mbar_init(BAR(25), R3_OUT_WARPS / 2);
+    for (int i = 0; i < R3_QCAP; ++i) mbar_init(qbar_s + 8u * i, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < R3_SCAN_WARPS) {
+    const int t = threadIdx.x;
+    constexpr int NT = 32 * R3_SCAN_WARPS;
+    float4* a = (float4*)(smem + P.off_aaug);
+    for (int i = t; i < 256; i += NT) {                   // ones block of the augmentation K-step (see the kernel above)
+      const int row = (i >> 3) & 7;
+      const float v = row < 3 ? 1.f : 0.f;
+      a[i] = make_float4(v, v, v, v);
+    }
+    for (int k = t; k < ktot; k += NT) perm_s[k] = (uint16_t)P.perm[k];
+    {
+      const float c1 = 0.001953125f * 1.03f;
+      const float c2 = (float)(R3_D + 16) * 4.76837158e-7f;
+      for (int c = t; c < P.nb * (P.BN >> 5); c += NT) {
+        const float rm = __uint_as_float(P.rmax[c]);
+        ((float*)(smem + P.off_ctab))[2 * c] = 0.5f * (c1 + c2) * rm;
+        ((float*)(smem + P.off_ctab))[2 * c + 1] = 0.5f * c2 * rm * rm + 1e-30f;
+      }
+    }
+    if (t < 8) qctl[t] = 0u;
+    if (STATS) for (int i = t; i < (P.K + 1) / 2; i += NT) hist[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles = (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == R3_W_PROD) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      const uint32_t ebytes = (uint32_t)P.nb * nD * P.BN * 128 + (uint32_t)P.nb * P.BN * 32;
+      mbar_expect_tx(BAR(0), ebytes);
+      for (int blk = 0; blk < P.nb; ++blk)
+        for (int c = 0; c < nD; ++c)
+          tma_load_2d(sbase + P.off_emain + (uint32_t)(blk * nD + c) * P.BN * 128, &emap, BAR(0), c * TC_DCH, blk * P.BN);
+      bulk_load_1d(sbase + P.off_eaug, P.eaug_img, (uint32_t)P.nb * P.BN * 32, BAR(0));
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int s = it & 1, ph = (it >> 1) & 1;
+        R3_WAIT_SLEEP(BAR(3 + s), ph ^ 1, 64, 0, it);
+        R3_EV(0, it);
+        mbar_expect_tx(BAR(1 + s), R3_ZSTAGE);
+        const int b = tile / P.tiles_per_img, pt = tile % P.tiles_per_img;
+        for (int c = 0; c < nD; ++c)
+          for (int grp = 0; grp < 4; ++grp)
+            tma_load_3d(sbase + P.off_z + s * R3_ZSTAGE + c * (TC_TILE * 128) + grp * 4096, &zmap, BAR(1 + s),
+                        pt * TC_TILE + grp * 32, c * TC_DCH, b);
+      }
+    }
+  } else if (warp == R3_W_MMA) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(P.BN);
+      mbar_wait(BAR(0), 0);
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        R3_WAIT_SLEEP(BAR(1 + s), ph, 32, 1, it);
+        R3_EV(1, it);
+        tc_fence_after();
+        const uint32_t zaddr = sbase + P.off_z + s * R3_ZSTAGE;
+        for (int blk = 0; blk < P.nb; ++blk, ++g) {
+          const int a = g & 1, aph = (g >> 1) & 1;
+          R3_WAIT_SLEEP(BAR(7 + a), aph ^ 1, 32, 2, it);
+          R3_EV(2 + blk, it);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_MAXBN;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int c = 0; c < nD; ++c) {
+            const uint32_t eaddr = sbase + P.off_emain + (uint32_t)(blk * nD + c) * P.BN * 128;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_desc(zaddr + c * (TC_TILE * 128) + ks * 1024, 4096, 512, 1);
+              const uint64_t bd = make_desc(eaddr + ks * 32, 16, 1024, 2);
+              umma_tf32(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+            }
+          }
+          {
+            const uint64_t ad = make_desc(sbase + P.off_aaug, 1024, 512, 1);
+            const uint64_t bd = make_desc(sbase + P.off_eaug + (uint32_t)blk * P.BN * 32, 128, 256, 0);
+            umma_tf32(d_tmem, ad, bd, idesc, acc);
+          }
+          umma_commit(BAR(5 + a));
+        }
+        umma_commit(BAR(3 + s));               // the tensor core is done reading this z stage
+      }
+    }
+  } else if (warp == R3_W_ZN) {
+    // ===================================== |z|^2 worker =====================================
+    // lane = pixels 4 lane .. 4 lane + 3, one 16-byte load per channel.
+    // Per pixel the same two ascending-d fma chains (even / odd channel quads) as everywhere in this library.
+    const uint32_t zrow0 = sbase + P.off_z + (uint32_t)(lane >> 3) * 4096;
+    uint32_t zx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zx[i] = (uint32_t)i * 128 + (uint32_t)(((lane & 7) ^ (i << 1)) << 4);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      R3_WAIT(BAR(1 + s), ph, 3, it);
+      uint32_t zc = zrow0 + s * R3_ZSTAGE;
+      float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01;
+#pragma unroll
+      for (int c = 0; c < nD; ++c) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = lds_v4(zc + jj * 512 + zx[i]);
+            if ((jj & 1) == 0) {
+              a01 = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), a01);
+              a23 = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), a23);
+            } else {
+              b01 = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), b01);
+              b23 = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), b23);
+            }
+          }
+        }
+        zc += 16384;
+      }
+      a01 = __fadd2_rn(a01, b01);
+      a23 = __fadd2_rn(a23, b23);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + P.off_zn + (uint32_t)((it % 3) * TC_TILE + 4 * lane) * 4),
+                   "f"(a01.x), "f"(a01.y), "f"(a23.x), "f"(a23.y) : "memory");
+      __syncwarp();
+      R3_EV(4, it);
+      if (lane == 0) { mbar_arrive(BAR(9 + (it % 3))); mbar_arrive(BAR(3 + s)); }
+    }
+  } else if (warp < R3_SCAN_WARPS) {
+    // ===================================== scan warps =======================================
+    // thread = (pixel, column group): maxima of its columns of both accumulator blocks, bounds, records; the results go to
+    // the `pub` slot (the output warps merge the two column groups and decide)
+    const int quad = warp & 3, cg = warp >> 2;
+    const int p = quad * 32 + lane;                       // pixel within the tile == TMEM lane
+    const uint32_t ctab_s = sbase + P.off_ctab;
+    const uint32_t pub_s = sbase + P.off_pub + (uint32_t)(cg * TC_TILE + p) * 16;
+    const int nchunks = P.BN >> 5;
+    const float rminbig = __uint_as_float(P.meta[1]);     // +inf when no code is excluded
+    int g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      R3Scan st;
+      st.L = -INFINITY; st.Urec = -INFINITY; st.cnt = 0; st.recA = 0; st.recB = 0;
+      // |z|^2 of this tile: ready long before the first accumulator block (same load, no tensor-core work in between)
+      R3_WAIT(BAR(9 + (it % 3)), (it / 3) & 1, 4, it);
+      const float z2 = lds_f32(sbase + P.off_zn + (uint32_t)((it % 3) * TC_TILE + p) * 4);
+      const float zn = sqrtf(z2) * 1.00001f;
+      for (int blk = 0; blk < P.nb; ++blk, ++g) {
+        const int a = g & 1, aph = (g >> 1) & 1;
+        float hm[16], R[8];
+        if (warp == 0) R3_EV(5 + 3 * blk, it);
+        R3_WAIT(BAR(5 + a), aph, 5, it);
+        if (warp == 0) R3_EV(6 + 3 * blk, it);
+        tc_fence_after();
+        if (cg < nchunks) r3_block_maxima(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)a * TC_MAXBN, cg, nchunks, hm, R);
+        tc_fence_before();
+        __syncwarp();
+        if (warp == 0) R3_EV(7 + 3 * blk, it);
+        if (lane == 0) mbar_arrive(BAR(7 + a));           // the accumulator block may be overwritten
+        if (cg < nchunks) r3_block_end(st, hm, R, cg, nchunks, blk, ctab_s, zn);
+      }
+      // flags: 1 overflow, 2 non-finite |z|^2, 4 an excluded ("big") code could still beat this group's lower bound
+      // (s_k <= r_k (2|z| - r_k), decreasing in r_k >= |z|)
+      uint32_t flags = st.cnt > 2 ? 1u : 0u;
+      if (!(z2 <= 3.0e38f)) flags |= 2u;
+      if (rminbig < 3.0e38f) {
+        const float lbest = 2.f * (st.L < 0.f ? st.L * 1.0009765625f : st.L);          // lower bound on the best exact 2 a_k
+        const float bigub = rminbig * (2.f * zn - rminbig);
+        if (!((rminbig >= zn) && (bigub + 1e-5f * (fabsf(bigub) + fabsf(lbest)) < lbest))) flags |= 4u;
+      }
+      const uint32_t w1 = f32_up16(st.Urec) | flags;
+      if (it > 0) R3_WAIT(BAR(24 + ((it - 1) & 1)), ((it - 1) >> 1) & 1, 6, it);     // the merging warps have read the slot (tile it - 1)
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pub_s), "r"(__float_as_uint(st.L)), "r"(w1),
+                   "r"(st.cnt >= 1 ? st.recA : 0u), "r"(st.cnt >= 2 ? st.recB : 0u) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(21 + (it & 1)));
+      if (warp == 0) R3_EV(14, it);
+    }
+  } else if (r3_out_index(warp) >= 0) {
+    // ===================================== output warps =====================================
+    // iteration j: merge(j) (my team's tiles only), then outputs(j - 2)
+    const int ow = r3_out_index(warp);
+    // outputs: pixels 4 pq .. 4 pq + 3 of the tile, channel quads co and co + 8 (channels 4 co .. + 3 and 32 + 4 co .. + 3);
+    // a quarter-warp = eight adjacent pixel quads of one channel = one 128-byte line of z / q
+    const int pq = 8 * (ow & 3) + (lane & 7), co = 4 * (ow >> 2) + (lane >> 3);
+    const uint32_t emain = sbase + P.off_emain;
+    float* sums_mine = nullptr;
+    if (STATS) {
+      const int rep = (int)(blockIdx.x % (unsigned)P.nrep);
+      sums_mine = (rep == 0 ? P.sums : P.sums_rep + (size_t)(rep - 1) * P.K * R3_D) + 4 * co;
+    }
+    const size_t hw = (size_t)P.HW;
+    const size_t off_out = (size_t)(4 * co) * hw + 4 * pq;         // my first channel row / pixel inside an image's tile
+    float2 lsA = make_float2(0.f, 0.f), lsB = lsA;
+    int tb = (int)blockIdx.x / P.tiles_per_img, tpt = (int)blockIdx.x % P.tiles_per_img;   // tile j
+    int b1 = 0, p01 = 0, b2 = 0, p02 = 0, b3 = 0, p03 = 0;                                 // tiles j - 1, j - 2, j - 3
+    mbar_wait(BAR(0), 0);                                 // codebook resident (read below with plain loads)
+    for (int it = 0; it < my_tiles + R3_LAG; ++it) {
+      const int b = tb, p0 = tpt * TC_TILE;
+      tpt += (int)gridDim.x;
+      while (tpt >= P.tiles_per_img) { tpt -= P.tiles_per_img; ++tb; }
+      // ---- merge(it) ------------------------------------------------------------------------------------
+      if (it < my_tiles && (ow >> 2) == (it & 1)) {
+        const int ws = it & (R3_WINS - 1), wph = (it / R3_WINS) & 1;
+        const int p = 32 * (ow & 3) + lane;
+        if ((ow & 3) == 0) R3_EV(11, it);
+        R3_WAIT_RELAXED(BAR(21 + (it & 1)), (it >> 1) & 1, 7, it);      // scan results of this tile
+        if ((ow & 3) == 0) R3_EV(12, it);
+        uint32_t pw[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pw[i][0]), "=r"(pw[i][1]), "=r"(pw[i][2]), "=r"(pw[i][3])
+                       : "r"(sbase + P.off_pub + (uint32_t)(i * TC_TILE + p) * 16) : "memory");
+        {
+          const uint32_t lb = __reduce_or_sync(0xffffffffu, pw[0][0] | pw[1][0] | pw[0][3] | pw[1][3]);
+          if (lane == 0) mbar_arrive(r3_after_loads(BAR(24 + (it & 1)), lb, PP.zero));      // the pub slot may be rewritten (tile it + 1)
+        }
+        const float Lg = fmaxf(__uint_as_float(pw[0][0]), __uint_as_float(pw[1][0]));
+        // flags of the scan threads (low bits of word 1): 1 overflow, 2 non-finite |z|^2, 4 an excluded ("big") code could
+        // still beat this group's own lower bound -- safe as soon as one group rules it out (its bound is <= the merged one)
+        bool ovf = false;
+        const bool bad = ((pw[0][1] | pw[1][1]) & 2u) != 0u;
+        const bool big_unsafe = (pw[0][1] & pw[1][1] & 4u) != 0u;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (__uint_as_float(pw[i][1] & 0xFFFF0000u) >= Lg) ovf |= (pw[i][1] & 1u) != 0;
+          else { pw[i][2] = 0; pw[i][3] = 0; }
+        }
+        const uint32_t c0 = pw[0][2], c1 = pw[0][3], c2 = pw[1][2], c3 = pw[1][3];     // records of column group 0, 0, 1, 1
+        const int total = r3_cells(c0) + r3_cells(c1) + r3_cells(c2) + r3_cells(c3);
+        bool fb = bad || ovf || total == 0 || big_unsafe || total > R3_MAXCAND;
+        bool defer = !fb && total > 1;
+        {   // at most 8 queued pixels per warp and tile (the queue holds R3_QCAP): the rest goes to the fallback list
+          const uint32_t dm = __ballot_sync(0xffffffffu, defer);
+          if (defer && __popc(dm & ((1u << lane) - 1u)) >= 8) { defer = false; fb = true; }
+        }
+        const int pp = p0 + p;
+        R3_WAIT_RELAXED(BAR(17 + ws), wph ^ 1, 8, it);    // every output warp has read this win slot (tile it - 4)
+        uint32_t wv1 = R3_WIN_SKIP;
+        if (fb) {
+          const int fslot = atomicAdd(P.fb_count, 1);
+          P.fb_rows[fslot] = b * P.HW + pp;
+        } else if (!defer) {
+          const uint32_t rec = c0 | c1 | c2 | c3;         // exactly one of them is non-zero
+          const int cgo = (c0 | c1) ? 0 : 1;
+          const int q = __clz((rec & 0x00FFFF00u) << 8), j = __clz(rec << 24);
+          const int w = r3_cell_pos(rec, cgo, q, j, bnsh);
+          uint32_t worig;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(worig) : "r"(sbase + P.off_perm + (uint32_t)w * 2));
+          wv1 = (uint32_t)w | (worig << 16);
+          int h, wc;
+          if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
+          else { h = pp / P.W; wc = pp - h * P.W; }
+          const size_t nb_ = (size_t)b * hw;
+          if (P.ids) store_id(P.ids + nb_, pp, h, wc, P.H, (int)worig, P.ids_mode);
+          if (P.ids_nat) P.ids_nat[nb_ + pp] = (int)worig;
+          if (STATS) atomicAdd(&hist[worig >> 1], (worig & 1u) ? 65536u : 1u);
+        }
+        if (!defer) asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s + (uint32_t)(ws * TC_TILE + p) * 4), "r"(wv1) : "memory");
+        // ---- queue the pixels with several candidate cells; their z rows are gathered with cp.async -----------
+        const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
+        if (dmask) {
+          const int n = __popc(dmask);
+          uint32_t base = 0;
+          if (lane == 0) {
+            base = atomicAdd((uint32_t*)&qctl[0], (uint32_t)n);
+            while ((int)(base + (uint32_t)n - qctl[1]) > R3_QCAP) {                    // space in the ring
+#ifdef VQ_R3_CHECK
+              if (*(volatile int*)&g_r3_abort) break;
+#endif
+              __nanosleep(100);
+            }
+          }
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (defer) {
+            const uint32_t slot = (base + (uint32_t)__popc(dmask & ((1u << lane) - 1u))) % R3_QCAP;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(queue_s + slot * R3_QSTRIDE + 256), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(qitp_s + slot * 4), "r"(((uint32_t)it << 7) | (uint32_t)p) : "memory");
+            __threadfence_block();
+          }
+          __syncwarp();
+          const float* zimg = P.z + (size_t)b * R3_D * hw + (size_t)lane * hw;       // channel `lane` of the image
+          uint32_t rank = 0;
+          for (uint32_t m = dmask; m; m &= m - 1u, ++rank) {
+            const int src = __ffs(m) - 1;
+            const int ppm = __shfl_sync(0xffffffffu, pp, src);
+            const uint32_t slot = (base + rank) % R3_QCAP;
+            const uint32_t dst = queue_s + slot * R3_QSTRIDE + (uint32_t)lane * 4;
+            cp_async4(dst, zimg + ppm);
+            cp_async4(dst + 128, zimg + 32 * hw + ppm);
+            cp_async_arrive(qbar_s + slot * 8);
+          }
+        }
+        __syncwarp();
+        const int ndec = 32 - __popc(dmask);
+        if (lane == 0 && ndec > 0) mbar_arrive_cnt(BAR(13 + ws), (uint32_t)ndec);
+        if ((ow & 3) == 0) R3_EV(13, it);
+      }
+      // ---- outputs(it - R3_LAG) ---------------------------------------------------------------------------
+      static_assert(R3_LAG == 3 && R3_LAG < R3_WINS, "tile bookkeeping below");
+      if (it >= R3_LAG) {
+        const int t = it - R3_LAG, ws = t & (R3_WINS - 1), wph = (t / R3_WINS) & 1;
+        if (ow == 0) R3_EV(15, t);
+        const size_t img = (size_t)b3 * R3_D * hw + p03 + off_out;
+        float4 z4[8];                                     // z4[i]: channel 4 co + i (i < 4), 32 + 4 co + i - 4 (i >= 4) of my four pixels
+        {
+          const float* zg = P.z + img;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            z4[i] = __ldg(reinterpret_cast<const float4*>(zg + (size_t)i * hw));
+            z4[4 + i] = __ldg(reinterpret_cast<const float4*>(zg + (size_t)(32 + i) * hw));
+          }
+        }
+        R3_WAIT_RELAXED(BAR(13 + ws), wph, 9, t);         // winners of the tile (decided by the merge, or by the straggler warp)
+        if (ow == 0) R3_EV(18, t);
+        uint32_t wv[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3])
+                     : "r"(win_s + (uint32_t)(ws * TC_TILE + 4 * pq) * 4) : "memory");
+        {
+          const uint32_t lb = __reduce_or_sync(0xffffffffu, wv[0] | wv[1] | wv[2] | wv[3]);
+          if (lane == 0) mbar_arrive(r3_after_loads(BAR(17 + ws), lb, PP.zero));     // the slot may be rewritten (tile t + 4)
+        }
+        float4 ea[4], eb[4];                              // code row of pixel x: channels 4 co .. + 3 and 32 + 4 co .. + 3
+        float msk[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const bool skip = (wv[x] & R3_WIN_SKIP) != 0u;
+          uint32_t w = skip ? 0u : (wv[x] & 0xFFFFu);
+#ifdef VQ_R3_CHECK
+          if (w >= (uint32_t)ktot || (!skip && ((wv[x] >> 16) & 0x7FFFu) >= (uint32_t)P.K)) { atomicAdd(P.fb_count + 2, 1); P.fb_count[3] = (int)wv[x]; P.fb_count[4] = t; w = 0u; }
+#endif
+          msk[x] = skip ? 0.f : 1.f;
+          const uint32_t kb = w >> bnsh, row = w & (uint32_t)(P.BN - 1);
+          const uint32_t er = emain + kb * (uint32_t)nD * bn128 + row * 128 + ((((uint32_t)co) ^ (row & 7)) << 4);
+          ea[x] = lds_v4(er);
+          eb[x] = lds_v4(er + bn128);
+        }
+        // q: one 16-byte store per channel, a quarter-warp writes one full 128-byte line; (z - q)^2
+        float* qo = P.q + img;
+        float2 l01 = make_float2(0.f, 0.f), l23 = l01;
+        const float2 m1 = make_float2(-1.f, -1.f);
+#define R3_CH(i, row_, F, C)                                                                             \
+        {                                                                                                \
+          const float4 qv = make_float4(F[0].C, F[1].C, F[2].C, F[3].C);                                 \
+          __stcs(reinterpret_cast<float4*>(qo + (size_t)(row_) * hw), qv);                               \
+          const float2 d01 = __ffma2_rn(make_float2(qv.x, qv.y), m1, make_float2(z4[i].x, z4[i].y));     \
+          const float2 d23 = __ffma2_rn(make_float2(qv.z, qv.w), m1, make_float2(z4[i].z, z4[i].w));     \
+          l01 = __ffma2_rn(d01, d01, l01);                                                               \
+          l23 = __ffma2_rn(d23, d23, l23);                                                               \
+        }
+        R3_CH(0, 0, ea, x) R3_CH(1, 1, ea, y) R3_CH(2, 2, ea, z) R3_CH(3, 3, ea, w)
+        R3_CH(4, 32, eb, x) R3_CH(5, 33, eb, y) R3_CH(6, 34, eb, z) R3_CH(7, 35, eb, w)
+#undef R3_CH
+        lsA = __ffma2_rn(l01, make_float2(msk[0], msk[1]), lsA);
+        lsB = __ffma2_rn(l23, make_float2(msk[2], msk[3]), lsB);
+        // EMA sums: equal codes among the four pixels are added up first
+        if (STATS) {
+          uint32_t wo[4];
+          bool live[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) { wo[x] = (wv[x] >> 16) & 0x7FFFu; live[x] = (wv[x] & R3_WIN_SKIP) == 0u; }
+          if (live[0] && live[1] && wo[0] == wo[1]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z4[i].x += z4[i].y;
+            live[1] = false;
+          }
+          if (live[2] && live[3] && wo[2] == wo[3]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z4[i].z += z4[i].w;
+            live[3] = false;
+          }
+          if (live[0] && live[2] && wo[0] == wo[2]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z4[i].x += z4[i].z;
+            live[2] = false;
+          }
+#define R3_RED(x, C)                                                                                              \
+          if (live[x]) {                                                                                         \
+            float* so = sums_mine + (size_t)wo[x] * R3_D;                                                        \
+            red_add_v4(so, z4[0].C, z4[1].C, z4[2].C, z4[3].C);                                                  \
+            red_add_v4(so + 32, z4[4].C, z4[5].C, z4[6].C, z4[7].C);                                             \
+          }
+          R3_RED(0, x) R3_RED(1, y) R3_RED(2, z) R3_RED(3, w)
+#undef R3_RED
+        }
+        if (ow == 0) R3_EV(19, t);
+      }
+      b3 = b2; p03 = p02; b2 = b1; p02 = p01; b1 = b; p01 = p0;
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicAdd((uint32_t*)&qctl[2], 1u); }     // no more queue entries from this warp
+    float lsum = (lsA.x + lsA.y) + (lsB.x + lsB.y);
+    lsum = warp_sum(lsum);
+    if (lane == 0 && P.loss_acc && lsum != 0.f) atomicAdd(P.loss_acc, (double)lsum);
+  } else if (warp == R3_W_STRAG) {
+    // ===================================== straggler warp ===================================
+    // Exact re-rank of the queued pixels.  A batch = the leading complete entries of the queue (<= 16).  Every lane pair
+    // (lp = lane & 15, channel-quad parity hf = lane >> 4) re-scores ONE (entry, candidate cell) per pass -- the cells of all
+    // entries of the batch are laid end to end, so a typical batch (6 entries x 2..3 cells) is one pass -- with the library's
+    // dot product (two ascending-d fma chains over the even / odd channel quads, joined by one addition); the best key of
+    // an entry is collected with a shared-memory atomicMax.
+    const int lp = lane & 15, hf = lane >> 4;
+    const uint32_t emain = sbase + P.off_emain;
+    const uint32_t perm_a = sbase + P.off_perm;
+    const size_t hw = (size_t)P.HW;
+    mbar_wait(BAR(0), 0);
+    uint32_t head = 0;
+    while (true) {
+      // entries head .. head + n - 1 have landed (their barriers, in order)
+      const uint32_t idx = head + (uint32_t)lp;
+      const uint32_t slot = idx % R3_QCAP;
+      const bool ready = mbar_test(qbar_s + slot * 8, (idx / R3_QCAP) & 1u);
+      const uint32_t rmask = __ballot_sync(0xffffffffu, ready) & 0xFFFFu;
+      const int n = min(__ffs(~rmask) - 1, R3_QCAP);      // leading run of complete entries
+      if (n == 0) {
+        if (qctl[2] == (uint32_t)R3_OUT_WARPS && qctl[0] == head) break;      // every merging warp is done and the queue is empty
+        __nanosleep(100);
+        continue;
+      }
+      // ---- setup: lane pair lp owns entry lp: records, number of cells, |z|^2 ---------------------------
+      const bool own = lp < n;
+      const uint32_t ent = queue_s + slot * R3_QSTRIDE;
+      uint32_t itp = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      float z2 = 0.f;
+      if (own) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(itp) : "r"(qitp_s + slot * 4) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(ent + 256) : "memory");
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {                     // |z|^2 = A + B: lane hf holds the channels of chain hf, ascending d
+          const float4 v = lds_v4(ent + (uint32_t)(2 * t + hf) * 16);
+          z2 = __fmaf_rn(v.x, v.x, z2); z2 = __fmaf_rn(v.y, v.y, z2); z2 = __fmaf_rn(v.z, v.z, z2); z2 = __fmaf_rn(v.w, v.w, z2);
+        }
+      }
+      z2 = __fadd_rn(z2, __shfl_xor_sync(0xffffffffu, z2, 16));
+      const int it = (int)(itp >> 7), p = (int)(itp & 127u);
+      const int it_lead = __shfl_sync(0xffffffffu, it, 0);
+      R3_EV(20, it_lead);
+      const int cnt = own ? r3_cells(c0) + r3_cells(c1) + r3_cells(c2) + r3_cells(c3) : 0;
+      int pre = cnt;                                      // inclusive prefix sum over the entries (lanes 0..15; both halves alike)
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o, 16);
+        if (lp >= o) pre += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, pre, 15, 16);
+      const int pre_ex = own ? pre - cnt : 0x7FFFFFFF;    // first flat cell index of my entry (entries beyond the batch: never matched)
+      if (own && hf == 0) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(qkey_s + (uint32_t)lp * 8), "r"(0u), "r"(0u) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(qz2_s + (uint32_t)lp * 4), "f"(z2) : "memory");
+      }
+      __syncwarp();
+      R3_EV(22, it_lead);
+      int niter = 0;
+      for (int f0 = 0; f0 < total; f0 += 16) {
+        ++niter;
+        const int fidx = f0 + lp;
+        const bool on = fidx < total;
+        // entry of flat cell fidx: the last entry whose first cell index is <= fidx (binary search over the lanes' pre_ex)
+        int ee = 0;
+#pragma unroll
+        for (int st = 8; st >= 1; st >>= 1) {
+          const int pc = __shfl_sync(0xffffffffu, pre_ex, ee + st, 16);
+          if (pc <= fidx) ee += st;
+        }
+        const int pe = __shfl_sync(0xffffffffu, pre_ex, ee, 16);
+        const uint32_t slot_e = (head + (uint32_t)ee) % R3_QCAP;
+        const uint32_t ent_e = queue_s + slot_e * R3_QSTRIDE;
+        float dot_o = 0.f, e2k_o = 0.f, z2e_o = 0.f;
+        uint32_t korig_o = 0u;
+        int k_o = 0;
+        if (on) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(ent_e + 256) : "memory");
+          // the j-th cell of the entry: record, then (quarter, residue) = (j / residues, j % residues) among the set bits
+          int j = fidx - pe, ri = 0;
+          uint32_t rec = r0;
+          int cr = r3_cells(r0);
+          if (j >= cr) { j -= cr; rec = r1; ri = 1; cr = r3_cells(r1);
+            if (j >= cr) { j -= cr; rec = r2; ri = 2; cr = r3_cells(r2);
+              if (j >= cr) { j -= cr; rec = r3; ri = 3; } } }
+          const uint32_t qm = __brev((rec >> 8) & 0xFFFFu) >> 16, rm = __brev(rec & 0xFFu) >> 24;     // bit q / bit j set: hot
+          const int nr = __popc(rm);
+          const int qi = j / nr, rj = j - qi * nr;
+          const int q = (int)__fns(qm, 0, qi + 1), jr = (int)__fns(rm, 0, rj + 1);
+          const int k = r3_cell_pos(rec, ri >> 1, q, jr, bnsh);
+          const int kb = k >> bnsh, row = k & (P.BN - 1);
+          const uint32_t eb = emain + (uint32_t)(kb * nD) * bn128 + (uint32_t)row * 128, r7 = (uint32_t)(row & 7) << 4;
+          uint32_t korig;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(korig) : "r"(perm_a + (uint32_t)k * 2));
+          const float e2k = lds_f32(sbase + P.off_eaug + (uint32_t)(((kb << bnsh) << 5) + (row >> 3) * 256 + (row & 7) * 16) + 12);
+          const float z2e = lds_f32(qz2_s + (uint32_t)ee * 4);
+          float dot = 0.f;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t jq = (uint32_t)(2 * t) + (uint32_t)hf;
+            const float4 zv = lds_v4(ent_e + jq * 16);
+            const float4 e4 = lds_v4(eb + (uint32_t)((2 * t) >> 3) * bn128 + (((jq & 7) << 4) ^ r7));
+            dot = __fmaf_rn(zv.x, e4.x, dot);
+            dot = __fmaf_rn(zv.y, e4.y, dot);
+            dot = __fmaf_rn(zv.z, e4.z, dot);
+            dot = __fmaf_rn(zv.w, e4.w, dot);
+          }
+          e2k_o = e2k; z2e_o = z2e; korig_o = korig; k_o = k;
+          dot_o = dot;
+        }
+        dot_o = __fadd_rn(dot_o, __shfl_xor_sync(0xffffffffu, dot_o, 16));      // A + B (commutative: same bits in both lanes)
+        if (on && hf == 0) {
+          const unsigned long long kc = ((unsigned long long)f32_orderable(ref_score(dot_o, e2k_o, z2e_o)) << 32) |
+                                        ((unsigned long long)(0xFFFFu - korig_o) << 16) | (unsigned long long)k_o;
+          atomicMax((unsigned long long*)(smem + (qkey_s - sbase) + (size_t)ee * 8), kc);        // ties: lowest ORIGINAL index
+        }
+        __syncwarp();
+      }
+      R3_EV(21, it_lead);
+#ifdef VQ_R3_TRACE
+      if (blockIdx.x == 0 && lane == 0 && it_lead < 64) { g_r3_trace[23 * 64 + it_lead] = niter; g_r3_trace[24 * 64 + it_lead] = n; }
+#endif
+      // ---- winners: win ring, code map, histogram ------------------------------------------------------
+      const int ws = it & (R3_WINS - 1);
+      if (own && hf == 0) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = tile / P.tiles_per_img, pp = (tile % P.tiles_per_img) * TC_TILE + p;
+        uint32_t klo, khi;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(klo), "=r"(khi) : "r"(qkey_s + (uint32_t)lp * 8) : "memory");
+        const int w = (int)(klo & 0xFFFFu);
+        const uint32_t worig = 0xFFFFu - (klo >> 16);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s + (uint32_t)(ws * TC_TILE + p) * 4), "r"((uint32_t)w | (worig << 16)) : "memory");
+        int h, wc;
+        if (P.w_shift >= 0) { h = pp >> P.w_shift; wc = pp & (P.W - 1); }
+        else { h = pp / P.W; wc = pp - h * P.W; }
+        const size_t nb_ = (size_t)b * hw;
+        if (P.ids) store_id(P.ids + nb_, pp, h, wc, P.H, (int)worig, P.ids_mode);
+        if (P.ids_nat) P.ids_nat[nb_ + pp] = (int)worig;
+        if (STATS) atomicAdd(&hist[worig >> 1], (worig & 1u) ? 65536u : 1u);
+      }
+      uint32_t am[R3_WINS];
+#pragma unroll
+      for (int i = 0; i < R3_WINS; ++i) am[i] = __ballot_sync(0xffffffffu, own && hf == 0 && ws == i);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+#pragma unroll
+        for (int i = 0; i < R3_WINS; ++i)
+          if (am[i]) mbar_arrive_cnt(BAR(13 + i), (uint32_t)__popc(am[i]));
+        qctl[1] = head + (uint32_t)n;                     // the entries may be overwritten
+      }
+      head += (uint32_t)n;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (STATS) {
+    for (int i = threadIdx.x; i < (P.K + 1) / 2; i += R3_THREADS) {
+      const uint32_t c = hist[i];
+      if (c & 0xFFFFu) red_add_s32(&P.counts[2 * i], (int)(c & 0xFFFFu));
+      if (c >> 16) red_add_s32(&P.counts[2 * i + 1], (int)(c >> 16));
+    }
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
@@ -1731,8 +2687,109 @@ static bool tcs_supported(int D, int K) { return tcs_geometry(D, K).ok; }
 
 static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s);
 
+// third-generation resident kernel (emb_dim 64, 257..512 codes): opt-in with VQ_B200_R3=1 in the environment.  Measured on
+// B200: 15 % faster than the default kernel on clustered input (few ambiguous pixels), slower on Gaussian /
+// post-ReLU input, where ~5 % of the pixels need the exact re-rank and its single straggler warp sets the pace
+static bool r3_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VQ_B200_R3"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on != 0;
+}
+static bool r3_supported(const FwdArgs& a) {
+  // the per-CTA histogram packs two 16-bit counters per word: a CTA must see fewer than 65536 pixels
+  const long long ntiles = (long long)a.B * ((long long)a.H * a.W / TC_TILE);
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 1;
+  if ((ntiles + sms - 1) / sms * TC_TILE >= 65536) return false;
+  return a.D == R3_D && r3_geometry(a.K).ok && r3_geometry(a.K).BN == TC_MAXBN && r3_geometry(a.K).nb == 2 && (a.H * a.W) % TC_TILE == 0 && r3_geometry(a.K).nb * r3_geometry(a.K).BN <= TC_SORT_MAX;
+}
+
+static int launch_assign_r3(const FwdArgs& a, cudaStream_t s) {
+  const int HW = a.H * a.W;
+  const R3Geom g = r3_geometry(a.K);
+  VQ_REQUIRE(g.ok && a.D == R3_D && HW % TC_TILE == 0, VQ_ERR_UNSUPPORTED, "tensor-core path (resident, emb_dim 64): unsupported shape");
+  VQ_REQUIRE(a.q != nullptr, VQ_ERR_INVALID_ARG, "tensor-core path: q must not be null");
+  EncodeTiledFn enc = get_encode_fn();
+  VQ_REQUIRE(enc != nullptr, VQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  VQ_REQUIRE((((uintptr_t)a.z) & 15) == 0 && (((uintptr_t)a.embed) & 15) == 0 && (((uintptr_t)a.q) & 15) == 0, VQ_ERR_INVALID_ARG,
+             "tensor-core path: z / embed / q must be 16-byte aligned");
+  CUtensorMap zmap, emap;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)a.D, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.D * HW * 4};
+    cuuint32_t box[3] = {32, TC_DCH, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_cached(enc, &zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.z, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(z) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.D, (cuuint64_t)(g.nb * g.BN)};
+    cuuint64_t strides[1] = {(cuuint64_t)a.D * 4};
+    cuuint32_t box[2] = {TC_DCH, (cuuint32_t)g.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_cached(enc, &emap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.ws.tc_es, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, VQ_ERR_CUDA, "cuTensorMapEncodeTiled(embed) failed: %d", (int)r);
+  }
+  float* eaug_img = a.ws.tc_aug;
+  uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
+  uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
+  const int ktot = g.nb * g.BN;
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+      a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+
+  R3Params PP{};
+  TcParams& P = PP.t;
+  P.z = a.z; P.E = a.embed; P.e2 = a.ws.e2; P.eaug_img = eaug_img; P.meta = meta;
+  P.perm = a.ws.tc_perm; P.rmax = rmax;
+  P.B = a.B; P.D = a.D; P.H = a.H; P.W = a.W; P.HW = HW; P.K = a.K;
+  P.BN = g.BN; P.nb = g.nb; P.nD = R3_ND; P.nst = 2;
+  P.bn_shift = 0;
+  while ((1 << P.bn_shift) < g.BN) ++P.bn_shift;
+  P.w_shift = -1;
+  if ((a.W & (a.W - 1)) == 0) { P.w_shift = 0; while ((1 << P.w_shift) < a.W) ++P.w_shift; }
+  P.tiles_per_img = HW / TC_TILE;
+  P.ntiles = a.B * P.tiles_per_img;
+  P.off_emain = (uint32_t)g.off_emain; P.off_eaug = (uint32_t)g.off_eaug; P.off_aaug = (uint32_t)g.off_aaug;
+  P.off_z = (uint32_t)g.off_z; P.off_pub = (uint32_t)g.off_pub; P.off_zn = (uint32_t)g.off_zn;
+  P.off_hist = (uint32_t)g.off_hist; P.off_perm = (uint32_t)g.off_perm; P.off_ctab = (uint32_t)g.off_ctab;
+  P.off_bar = (uint32_t)g.off_bar;
+  PP.off_win = (uint32_t)g.off_win; PP.off_queue = (uint32_t)g.off_queue; PP.zero = 0u;
+  P.ids = a.ids; P.ids_nat = a.ids_nat; P.q = a.q; P.loss_acc = a.ws.loss_acc;
+  P.counts = a.stats ? a.ws.counts : nullptr;
+  P.sums = a.stats ? a.stats + stats_sums_offset(a.K) : nullptr;
+  P.sums_rep = a.ws.sums_rep;
+  P.nrep = tc_sums_replicas(a.K, a.D);
+  P.fb_count = a.ws.misc; P.fb_rows = a.ws.fb_rows;
+  P.ids_mode = ids_mode_of(a.flags);
+  P.dbg = nullptr;
+
+  int grid = sm_count_tc();
+  if (grid > P.ntiles) grid = P.ntiles;
+  const bool stats = a.stats != nullptr;
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const R3Params);
+  KernFn kern = stats ? vq_assign_r3_kernel<true> : vq_assign_r3_kernel<false>;
+  static bool attr_set[kMaxDevices][2] = {};
+  const int dev = current_device();
+  if (!attr_set[dev][stats ? 1 : 0]) {
+    VQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_set[dev][stats ? 1 : 0] = true;
+  }
+  const bool prof = profile_begin(s);
+  kern<<<grid, R3_THREADS, g.total, s>>>(zmap, emap, PP);
+  if (prof) profile_end(s);
+  count_launch();
+  VQ_CUDA_CHECK(cudaGetLastError());
+  return VQ_OK;
+}
+
 int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   const int HW = a.H * a.W;
+  if (!dbg && r3_enabled() && r3_supported(a)) return launch_assign_r3(a, s);
   const TcGeom g = tc_geometry(a.D, a.K);
   // resident codebook only when two z stages fit beside it (one stage = no prefetch: D = 256 at K = 64 ran 1.5x slower
   // than the streamed kernel)
@@ -1971,6 +3028,20 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
 int launch_assign_tc(const FwdArgs& a, cudaStream_t s) { return launch_assign_tc_impl(a, nullptr, s); }
 
 int tc_debug_timing(long long* host_out, int n) {
+#ifdef VQ_R3_CHECK
+  {
+    const int tot3 = 32 * 64;
+    if (n < tot3) return -1;
+    if (cudaMemcpyFromSymbol(host_out, g_r3_dbg, sizeof(long long) * tot3) != cudaSuccess) return -2;
+    return tot3;
+  }
+#endif
+#ifdef VQ_R3_TRACE
+  const int tot3 = 32 * 64;
+  if (n < tot3) return -1;
+  if (cudaMemcpyFromSymbol(host_out, g_r3_trace, sizeof(long long) * tot3) != cudaSuccess) return -2;
+  return tot3;
+#endif
 #ifdef VQ_TC_TIMING
   const int tot = 148 * 16 * 8;
   if (n < tot) return -1;
