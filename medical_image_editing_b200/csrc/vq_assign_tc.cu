@@ -104,9 +104,10 @@ static TcGeom tc_geometry(int D, int K) {
 }
 
 int tc_sums_replicas(int K, int D) {
-  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 4 MB in total (the replicas
-  // are zeroed by vq_prep_kernel and folded by vq_finish_kernel on every call)
-  size_t r = ((size_t)4 << 20) / ((size_t)K * D * 4);
+  // enough replicas that concurrent CTAs rarely reduce into the same L2 line, capped at 16 MB in total (the replicas
+  // are zeroed by vq_prep_kernel and folded by vq_finish_kernel on every call: a few microseconds; with 4 MB -- 8
+  // replicas at K = 512, D = 256 -- a skewed code usage (post-ReLU input) serialised the reductions of the hot rows in L2)
+  size_t r = ((size_t)16 << 20) / ((size_t)K * D * 4);
   if (r > (size_t)TC_MAX_REP) r = TC_MAX_REP;
   if (r < 1) r = 1;
   return (int)r;
@@ -2545,8 +2546,14 @@ vq_assign_tcs_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_cons
           const size_t nb_ = (size_t)b * hw;
           if (P.ids) store_id(P.ids + nb_, pp, h, wc, P.H, (int)worig, P.ids_mode);
           if (P.ids_nat) P.ids_nat[nb_ + pp] = worig;
-          if (STATS) atomicAdd(&P.counts[worig], 1);
         }
+      }
+      if (STATS) {
+        // histogram: the pixels of the warp that chose the same code share one atomic (a million single increments on
+        // 512 addresses serialise in L2 -- worst when a few codes take most of the pixels)
+        const int key = (hf == 0 && !fb) ? (int)worig : -1 - lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&P.counts[key], __popc(grp));
       }
       {
         const bool live = !fb;
