@@ -26,7 +26,7 @@ REDUCE_MODES = ("sum", "mean", "reference")
 
 _WORKSPACES = {}
 _SIDE_STREAMS = {}        # device index -> stream of the overlapped statistics exchange
-_PENDING = {}             # embed.data_ptr() -> event recorded after an overlapped all-reduce + EMA update
+_PENDING = {}             # embed.data_ptr() -> (event recorded after an overlapped all-reduce + EMA update, recorded under capture?)
 
 
 def _side_stream(device: torch.device) -> "torch.cuda.Stream":
@@ -46,11 +46,22 @@ def wait_pending_update(embed: torch.Tensor) -> None:
     if not embed.is_cuda:
         return
     key = embed.data_ptr()
-    ev = _PENDING.get(key)
-    if ev is not None:
-        torch.cuda.current_stream(embed.device).wait_event(ev)
-        if ev.query():                  # finished: later readers on any stream need no dependency
-            _PENDING.pop(key, None)
+    entry = _PENDING.get(key)
+    if entry is None:
+        return
+    ev, captured = entry
+    capturing = torch.cuda.is_current_stream_capturing()
+    if captured != capturing:
+        # An event recorded inside a CUDA-graph capture only exists inside that graph (waiting on it from eager code is
+        # cudaErrorInvalidValue), and eager work of before the capture has long finished when the graph is replayed:
+        # either way there is nothing to wait for.  (The capture itself joins the side stream before it ends.)
+        _PENDING.pop(key, None)
+        return
+    torch.cuda.current_stream(embed.device).wait_event(ev)
+    if capturing:
+        _PENDING.pop(key, None)         # inside a capture the dependency is now an edge of the graph (no event queries there)
+    elif ev.query():                    # finished: later readers on any stream need no dependency
+        _PENDING.pop(key, None)
 
 
 
@@ -162,7 +173,7 @@ def _exchange_and_update(embed, cluster_size, embed_avg, stats, momentum, eps, r
             done.record(side)
         for t_ in (stats, scratch):
             t_.record_stream(side)
-        _PENDING[embed.data_ptr()] = done
+        _PENDING[embed.data_ptr()] = (done, torch.cuda.is_current_stream_capturing())
     else:
         run(scratch_main, _stream())
 
