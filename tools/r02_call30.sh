@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out/r02c30
+O=gpurun_out/r02c30
+export VQ_B200_R3=1
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1 || { echo "SMOKE FAILED"; tail -20 $O/smoke.log; exit 1; }
+timeout 60 python tools/r3_check.py noise 2 1 > $O/check0.log 2>&1 || { echo "CHECK FAILED/HUNG"; tail -5 $O/check0.log | cut -c1-300; exit 1; }
+cut -c1-60,100-200 $O/check0.log
+{
+timeout 100 python tools/ab.py 64 512 16 noise
+timeout 100 python tools/ab.py 64 512 16 clustered
+timeout 100 python tools/ab.py 64 512 16 relu
+} > $O/ab.log 2>&1
+cat $O/ab.log
+VQ_B200_LIB=build_variants/lib_r3trace.so timeout 100 python tools/r3_trace.py 64 512 16 0 noise > $O/trace.log 2>&1
+grep -v "^  tile\|^tiles 20" $O/trace.log
+timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q --timeout 60 > $O/pytest.log 2>&1; tail -3 $O/pytest.log
