@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -908,6 +909,61 @@ int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int3
   return VQ_OK;
 }
 
+// Same gather, 64 a x 16 c tiles (A % 4 == 0, out 16-byte aligned): every (channel, c) row of the tile is 256 contiguous
+// bytes of the output (the 32 x 32 tile wrote 128-byte pieces 2 KB apart: poor DRAM page locality for a pure write
+// stream), the ids are still read in full 128-byte rows.  thread = four consecutive a of one c.
+template <int TA, int TC>
+__global__ void __launch_bounds__(256)
+vq_lookup_nchw_tw_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, int K, int D,
+                          float* __restrict__ out, int B, int A, int C, int* __restrict__ status) {
+  static_assert(TA * TC == 1024 && TA % 4 == 0, "256 threads x 4 pixels");
+  __shared__ int sid[TA][TC + 1];
+  const int a0 = blockIdx.x * TA, c0 = blockIdx.y * TC, b = blockIdx.z;
+  {
+    const int lc = threadIdx.x % TC, la = threadIdx.x / TC;           // TC consecutive c (one row of int64) x 256 / TC a per pass
+#pragma unroll
+    for (int r = 0; r < TA; r += 256 / TC) {
+      const int a = a0 + r + la, c = c0 + lc;
+      int v = -1;
+      if (a < A && c < C) {
+        const long long id = ids[((long long)b * A + a) * C + c];
+        if (id >= 0 && id < K) v = (int)id;
+        else if (status) *status = 1;
+      }
+      sid[r + la][lc] = v;
+    }
+  }
+  __syncthreads();
+  const int a4 = (threadIdx.x % (TA / 4)) * 4, cc = threadIdx.x / (TA / 4);
+  const int a = a0 + a4, c = c0 + cc;
+  if (a >= A || c >= C) return;                          // A % 4 == 0: the quad is inside or outside as a whole
+  const int i0 = sid[a4][cc], i1 = sid[a4 + 1][cc], i2 = sid[a4 + 2][cc], i3 = sid[a4 + 3][cc];
+  const float* e0 = E + (size_t)(i0 < 0 ? 0 : i0) * D;
+  const float* e1 = E + (size_t)(i1 < 0 ? 0 : i1) * D;
+  const float* e2 = E + (size_t)(i2 < 0 ? 0 : i2) * D;
+  const float* e3 = E + (size_t)(i3 < 0 ? 0 : i3) * D;
+  const bool v0 = i0 >= 0, v1 = i1 >= 0, v2 = i2 >= 0, v3 = i3 >= 0;       // ids outside [0, K): zeros (and `status`)
+  float* o = out + (((long long)b * D) * C + c) * A + a;
+  const long long dstride = (long long)C * A;
+  int d = 0;
+  if ((D & 3) == 0 && ((((uintptr_t)E) & 15) == 0)) {
+#pragma unroll 4
+    for (; d + 4 <= D; d += 4) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(e0 + d));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(e1 + d));
+      const float4 r2 = __ldg(reinterpret_cast<const float4*>(e2 + d));
+      const float4 r3 = __ldg(reinterpret_cast<const float4*>(e3 + d));
+      __stcs(reinterpret_cast<float4*>(o + (d + 0) * dstride), make_float4(v0 ? r0.x : 0.f, v1 ? r1.x : 0.f, v2 ? r2.x : 0.f, v3 ? r3.x : 0.f));
+      __stcs(reinterpret_cast<float4*>(o + (d + 1) * dstride), make_float4(v0 ? r0.y : 0.f, v1 ? r1.y : 0.f, v2 ? r2.y : 0.f, v3 ? r3.y : 0.f));
+      __stcs(reinterpret_cast<float4*>(o + (d + 2) * dstride), make_float4(v0 ? r0.z : 0.f, v1 ? r1.z : 0.f, v2 ? r2.z : 0.f, v3 ? r3.z : 0.f));
+      __stcs(reinterpret_cast<float4*>(o + (d + 3) * dstride), make_float4(v0 ? r0.w : 0.f, v1 ? r1.w : 0.f, v2 ? r2.w : 0.f, v3 ? r3.w : 0.f));
+    }
+  }
+  for (; d < D; ++d)
+    __stcs(reinterpret_cast<float4*>(o + d * dstride),
+           make_float4(v0 ? __ldg(e0 + d) : 0.f, v1 ? __ldg(e1 + d) : 0.f, v2 ? __ldg(e2 + d) : 0.f, v3 ? __ldg(e3 + d) : 0.f));
+}
+
 int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, float* out, int layout, int B,
                   int A, int C, int* status, cudaStream_t s) {
   if (n == 0) return VQ_OK;
@@ -923,7 +979,18 @@ int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int 
     vq_lookup_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(ids, n, embed, K, D, out, status);
   } else {
     dim3 grid((A + 31) / 32, (C + 31) / 32, B);
-    if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0)
+    static int t64 = -1;
+    if (t64 < 0) { const char* e = getenv("VQ_LOOKUP_T64"); t64 = e ? atoi(e) : 1; }
+    if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 1) {
+      dim3 g64((A + 63) / 64, (C + 15) / 16, B);
+      vq_lookup_nchw_tw_kernel<64, 16><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+    } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 2) {
+      dim3 g64((A + 127) / 128, (C + 7) / 8, B);
+      vq_lookup_nchw_tw_kernel<128, 8><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+    } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 3) {
+      dim3 g64((A + 255) / 256, (C + 3) / 4, B);
+      vq_lookup_nchw_tw_kernel<256, 4><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+    } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0)
       vq_lookup_nchw_t_kernel<true><<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
     else
       vq_lookup_nchw_t_kernel<false><<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
