@@ -184,6 +184,76 @@ def run_cpu_baseline(wl, budget_s=12.0, slices=1):
                       f"on the host cores, median of {len(times)} steps, {med * 1e3:.1f} ms/step"}
 
 
+def run_reference_on_gpu(wl, dev, vq_b200, steps=3):
+    """Sanity / noise-floor leg: the UNMODIFIED reference `VQModule` run by stock torch-CUDA on the same
+    B200, same seeded input and EMA state as the B200 arm -- training step (forward + EMA + backward) time, and how many
+    code ids of an eval forward differ between the reference's fp32 cuBLAS GEMM + topk and this library (ties /
+    rounding of the reference's own GEMM: the noise floor of 'bit-exact ids').  None when no copy of the reference is
+    reachable.  Part of the baseline legs: nothing of it runs inside the timed regions of the B200 arm."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            return None
+        RefVQ = ref_loader.load_reference_vq()
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    B, D, H, K = wl["B"], wl["D"], wl["H"], wl["K"]
+    n = B * H * H
+    if n * K * 16 > 60e9:                                          # N x K one-hot (int64 + fp32) + K x N scores must fit
+        return {"skipped": f"reference scratch for N = {n}, K = {K} would need {n * K * 16 / 1e9:.0f} GB"}
+    os.environ["WORLD_SIZE"] = os.environ.get("WORLD_SIZE", "1")
+    try:
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        gen = torch.Generator(device=dev).manual_seed(4242)
+        ref = RefVQ(emb_dim=D, dict_size=K, momentum=CFG["momentum"], eps=CFG["eps"], knn_backend="torch").to(dev)
+        with torch.no_grad():
+            ref.embed.copy_(vq_b200.embed)
+            ref.cluster_size.copy_(vq_b200.cluster_size)
+            ref.embed_avg.copy_(vq_b200.embed_avg)
+        z = torch.randn(B, D, H, H, device=dev, generator=gen)
+        g_q = torch.randn(B, D, H, H, device=dev, generator=gen)
+        one = torch.ones((), device=dev)
+        # eval forward of both on the same input: differing ids
+        ref.eval()
+        was_training = vq_b200.training
+        vq_b200.eval()
+        with torch.no_grad():
+            _, loss_r, ids_r = ref(z)
+            _, loss_b, ids_b = vq_b200(z)
+        vq_b200.train(was_training)
+        differ = int((ids_r != ids_b).sum().item())
+        loss_rel = abs(float(loss_r) - float(loss_b)) / max(abs(float(loss_r)), 1e-30)
+        del ids_r, ids_b
+        ref.train(True)
+
+        def step():
+            zz = z.detach().requires_grad_(True)
+            q, loss, ids = ref(zz)
+            torch.autograd.grad((q, loss), zz, (g_q, one))
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        del ref, z, g_q
+        torch.cuda.empty_cache()
+        return {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "what": "the unmodified reference VQModule (vq_module.py:139-211) under stock torch-CUDA (fp32 cuBLAS, "
+                        "allow_tf32 off) on this GPU: quantiser train step, same shape / EMA state as the B200 arm",
+                "eval_ids_differing_from_b200": differ, "eval_loss_rel_diff": loss_rel, "lookups": n,
+                "peak_memory_gb": peak_gb, "torch": torch.__version__}
+    except Exception as exc:
+        torch.cuda.empty_cache()
+        return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 def run_reference_arm(args, wl, wl_name):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -585,7 +655,7 @@ def run_b200_arm(args, wl, wl_name):
     if wl_name == "config2" and not args.no_model:
         try:
             wnet = measure_wnet_b200(dev, rank, world, steps=max(3, min(args.steps, 10)), warmup=3,
-                                     inline_exchange=args.inline_exchange)
+                                     inline_exchange=args.inline_exchange, fused_norm=args.fused_norm)
         except Exception as exc:                                 # never lose the headline line to the model leg
             if world > 1:
                 raise
@@ -614,6 +684,8 @@ def run_b200_arm(args, wl, wl_name):
                          "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                          "peak_source": f"MEASURED_PEAKS.json ({which})"})
         cpu = run_cpu_baseline(wl) if (world == 1 and not args.no_cpu) else None
+        if cpu is not None:
+            cpu["reference_on_gpu"] = run_reference_on_gpu(wl, dev, vq)
         if isinstance(wnet, dict) and "error" not in wnet and world == 1 and not args.no_cpu:
             try:
                 wnet["cpu_baseline"] = run_cpu_wnet_baseline(budget_s=12.0)
@@ -698,7 +770,18 @@ def wnet_images(n, B, H, seed, pin=False):
     return [t.pin_memory() for t in out] if pin else out
 
 
-def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, name="vqwnet"):
+def fuse_wnet_norms(model, mode):
+    """--fused-norm: swap InstanceNorm2d + ReLU pairs of the harness for the fused CUDA pair:
+    'tail' = the pair that produces the quantiser's input (end of the first U-Net's last up stage), 'all' = every pair."""
+    from medical_image_editing_b200.src.functions import fuse_norm_relu_pairs
+    if mode == "tail":
+        return fuse_norm_relu_pairs(model.first.up[-1].body, only_last=True)
+    if mode == "all":
+        return sum(fuse_norm_relu_pairs(m) for m in [m for m in model.modules() if isinstance(m, torch.nn.Sequential)])
+    return 0
+
+
+def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, name="vqwnet", fused_norm="none"):
     """VQ-W-Net train slices/s on this rank's GPU (data parallel over `world` ranks).  Returns a dict on rank 0."""
     import torch.distributed as dist
     import medical_image_editing_b200 as pkg
@@ -712,6 +795,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, na
     model = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch",
                                             reduce_mode="sum", overlap_exchange=(world > 1 and not inline_exchange)),
                         1, dict_size=WNET["K"]).to(dev)
+    n_fused = fuse_wnet_norms(model, fused_norm)
     trainer = DataParallelVQTrainer(model, lr=WNET["lr"], commit_weight=WNET["commit_weight"])
     host = wnet_images(4, B, H, 4321 + rank, pin=True)
     resident = [t.to(dev) for t in host]
@@ -778,6 +862,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, na
                                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel": "vq_assign_tc",
                                             "peak_source": f"MEASURED_PEAKS.json ({which})"}),
         "replicas_in_sync": bool(in_sync), "final_loss": losses[-1] if losses else None,
+        "fused_norm": fused_norm, "fused_norm_pairs": n_fused,
     }
 
 
@@ -875,7 +960,8 @@ def run_wnet_b200_arm(args):
     dev = torch.device("cuda", local)
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
-    r = measure_wnet_b200(dev, rank, world, args.steps, args.warmup, args.inline_exchange, name=args.workload)
+    r = measure_wnet_b200(dev, rank, world, args.steps, args.warmup, args.inline_exchange, name=args.workload,
+                          fused_norm=args.fused_norm)
     t1 = time.time()
     if rank == 0:
         clocks = sampler.stop(t0, t1)
@@ -886,7 +972,8 @@ def run_wnet_b200_arm(args):
                "scaling": "strong" if args.workload == "vqwnet512" else "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wnet_config(world, name=args.workload),
                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": r["roofline"],
-               "cpu_baseline": cpu, "replicas_in_sync": r["replicas_in_sync"], "final_loss": r["final_loss"]}
+               "cpu_baseline": cpu, "replicas_in_sync": r["replicas_in_sync"], "final_loss": r["final_loss"],
+               "fused_norm": r["fused_norm"], "fused_norm_pairs": r["fused_norm_pairs"]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -905,6 +992,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
     ap.add_argument("--inline-exchange", action="store_true", help="N > 1: all-reduce + EMA update on the compute stream")
+    ap.add_argument("--fused-norm", default="none", choices=["none", "tail", "all"],
+                    help="VQ-W-Net legs: InstanceNorm2d + ReLU pairs run by vq_norm_relu_fwd/bwd (tail = the quantiser's producer)")
     ap.add_argument("--no-graphs", action="store_true", help="eager step loop in the timed region instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -166,6 +166,18 @@ int vq_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels
 int vq_onehot(const void* labels, int label_bytes, int64_t B, int64_t HW, int C, float* out, vq_stream_t stream);
 
 /*
+ * The two layers in front of the quantiser: `nn.InstanceNorm2d(C)` (no affine parameters, no running
+ * statistics, biased variance, eps inside the square root) followed by `nn.ReLU` -- the end of `up_conv1_1.double_conv`
+ * (reference blocks.py:39-50), whose output is the z the quantiser reads (vqwnet.py:104-109).
+ *   x      [B, C, H, W] fp32 NCHW (the convolution output);  z [B, C, H, W]: relu((x - mean) * rstd), written once;
+ *   stats  float [B*C][2] = {mean, rstd} per plane, written by the forward for the backward (may be NULL in inference);
+ *   vq_norm_relu_bwd: g_x from g_z, the saved x and stats (the relu mask is recomputed from x exactly as the forward did).
+ */
+int vq_norm_relu_fwd(const float* x, float* z, float* stats, int B, int C, int H, int W, float eps, vq_stream_t stream);
+int vq_norm_relu_bwd(const float* g_z, const float* x, const float* stats, float* g_x, int B, int C, int H, int W,
+                     vq_stream_t stream);
+
+/*
  * Measurement hooks (used by bench.py only; they do not change results).
  *   vq_launch_count     number of kernels this library has launched in this process so far.
  *   vq_profile_enable   when on, vq_assign_fwd brackets its dominant kernel (the nearest-code

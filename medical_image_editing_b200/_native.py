@@ -51,6 +51,8 @@ SIGNATURES = {
     "vq_onehot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_f32p, ctypes.c_void_p]),
     "vq_embed_loss_bwd": (ctypes.c_int, [c_f32p, c_f32p, c_i32p, c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 5 +
                           [ctypes.c_void_p]),
+    "vq_norm_relu_fwd": (ctypes.c_int, [c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]),
+    "vq_norm_relu_bwd": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]),
     "vq_launch_count": (ctypes.c_int64, []),
     "vq_debug_tc_ncols": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "vq_debug_tc_scores": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32p,

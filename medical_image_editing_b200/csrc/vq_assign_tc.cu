@@ -2046,7 +2046,7 @@ struct TcsGeom {
   bool ok;
 };
 constexpr int TCS_QST_BYTES = 16 * TC_DCH * 4;      // q staging box of one epilogue warp: 16 pixels x 32 channels
-constexpr int TCS_MAX_ND = 8;       // D <= 256
+constexpr int TCS_MAX_ND = 16;      // D <= 512 (VQGAN: emb_dim 512, vqgan.py:389-390)
 constexpr int TCS_MAX_ST = 8;       // ring stages
 constexpr int TCS_MAXCAND = 16;     // candidates re-scored exactly per pixel (large codebooks tie more often)
 // barrier slots of the streaming kernel

@@ -147,6 +147,25 @@ int vq_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int D, f
   return launch_lookup(ids, n, embed, K, D, out, layout, B, A, C, status, (cudaStream_t)stream);
 }
 
+int vq_norm_relu_fwd(const float* x, float* z, float* stats, int B, int C, int H, int W, float eps, vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0 && eps >= 0.f, VQ_ERR_INVALID_ARG, "vq_norm_relu_fwd: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  const long long planes = (long long)B * C, HW = (long long)H * W;
+  if (planes == 0 || HW == 0) return VQ_OK;
+  VQ_REQUIRE(x && z, VQ_ERR_INVALID_ARG, "vq_norm_relu_fwd: null pointer");
+  return launch_norm_relu_fwd(x, z, stats, planes, HW, eps, (cudaStream_t)stream);
+}
+
+int vq_norm_relu_bwd(const float* g_z, const float* x, const float* stats, float* g_x, int B, int C, int H, int W,
+                     vq_stream_t stream) {
+  set_error("");
+  VQ_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, VQ_ERR_INVALID_ARG, "vq_norm_relu_bwd: bad shape");
+  const long long planes = (long long)B * C, HW = (long long)H * W;
+  if (planes == 0 || HW == 0) return VQ_OK;
+  VQ_REQUIRE(g_z && x && stats && g_x, VQ_ERR_INVALID_ARG, "vq_norm_relu_bwd: null pointer");
+  return launch_norm_relu_bwd(g_z, x, stats, g_x, planes, HW, (cudaStream_t)stream);
+}
+
 int vq_debug_tc_ncols(int D, int K) { return tc_debug_ncols(D, K); }
 
 int vq_debug_tc_timing(long long* host_out, int n) { return tc_debug_timing(host_out, n); }

@@ -133,6 +133,11 @@ int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* em
 int launch_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* labels, const float* embed,
                           const float* weights, float* g_z, int B, int D, int H, int W, int K, cudaStream_t s);
 
+// vq_norm_relu.cu: InstanceNorm2d + ReLU in front of the quantiser
+int launch_norm_relu_fwd(const float* x, float* z, float* stats, long long planes, long long HW, float eps, cudaStream_t s);
+int launch_norm_relu_bwd(const float* g_z, const float* x, const float* stats, float* g_x, long long planes, long long HW,
+                         cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------

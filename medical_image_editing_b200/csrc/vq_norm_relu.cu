@@ -1,0 +1,299 @@
+// vq_norm_relu.cu -- the U-Net tail that produces the quantiser's input (sm_100a only).
+//
+// The last two layers in front of `VQModule` are `nn.InstanceNorm2d(C)` + `nn.ReLU(inplace=True)` (the end of
+// `up_conv1_1.double_conv`, reference blocks.py:39-50, vqwnet.py:104-108).  Stock torch runs them as batch-norm statistics +
+// normalise (x read twice, y written) and an in-place ReLU (y read and written): five N*D-sized passes in the forward and
+// seven in the backward.  z itself must exist in HBM -- the networks return it as `embed` (vqwnet.py:108) and the stage-1
+// trainers feed it to EmbeddingLoss -- so the fusion that is left is on the producer side: z is written ONCE, straight
+// from the convolution output.
+//
+// Layout: NCHW fp32; a (b, c) plane is HW contiguous floats.  A plane is handled by a thread-block CLUSTER of S CTAs
+// (S = 1, 2, 4, 8; one segment of the plane each): pass 1 reads the segment and reduces shifted sums, the partial sums
+// are exchanged through distributed shared memory, pass 2 re-reads the segment -- which is still in L2: the launcher
+// sizes segments and the persistent grid so that all segments in flight fit in the 126 MB L2 -- and writes the result.
+// DRAM traffic is therefore the minimum: forward read x + write z, backward read x, g_z + write g_x.
+#include <cooperative_groups.h>
+
+#include "vq_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace vqb200 {
+namespace {
+
+constexpr int NR_THREADS = 512;
+constexpr int NR_WARPS = NR_THREADS / 32;
+constexpr int NR_MAX_CLUSTER = 8;
+
+struct NrPlan {
+  int S;            // cluster size = segments per plane
+  long long seg;    // floats per segment (multiple of 4 when the vector path is used)
+  int clusters;     // persistent clusters in the grid
+};
+
+// Segments of at most `seg_max` floats, so that (CTAs in flight) x (bytes a CTA streams per plane) stays below L2.
+NrPlan nr_plan(long long planes, long long HW, bool vec, long long seg_max) {
+  NrPlan p;
+  p.S = 1;
+  while (p.S < NR_MAX_CLUSTER && (HW + p.S - 1) / p.S > seg_max) p.S <<= 1;
+  long long seg = (HW + p.S - 1) / p.S;
+  if (vec) seg = (seg + 3) / 4 * 4;
+  p.seg = seg;
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+  long long ctas = 2LL * sms;                               // two CTAs of 512 threads per SM
+  long long clusters = ctas / p.S;
+  if (clusters > planes) clusters = planes;
+  if (clusters < 1) clusters = 1;
+  p.clusters = (int)clusters;
+  return p;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float nr_gx(float xv, float gv, float mean, float rstd, float m1, float m2) {
+  const float xh = (xv - mean) * rstd;
+  const float gy = xh > 0.f ? gv : 0.f;
+  return rstd * ((gy - m1) - xh * m2);
+}
+
+// sum over the cluster of two doubles per CTA; every CTA gets the totals.  `slot` is this CTA's shared-memory pair.
+__device__ __forceinline__ void cluster_sum2(double (&v)[2], double* slot, double* warp_part, int nranks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
+  }
+  if (lane == 0) { warp_part[2 * warp] = v[0]; warp_part[2 * warp + 1] = v[1]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < NR_WARPS; ++w) { a += warp_part[2 * w]; b += warp_part[2 * w + 1]; }
+    slot[0] = a; slot[1] = b;
+  }
+  if (nranks > 1) {
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();                                              // partial sums of every CTA are visible cluster-wide
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < nranks; ++r) {                      // same order in every CTA: identical totals
+      const double* rs = cl.map_shared_rank(slot, r);
+      a += rs[0]; b += rs[1];
+    }
+    v[0] = a; v[1] = b;
+    cl.sync();                                              // nobody overwrites its slot (next plane) while a peer still reads it
+  } else {
+    __syncthreads();
+    v[0] = slot[0]; v[1] = slot[1];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward: z = relu((x - mean) * rstd), mean / biased variance over the plane, rstd = 1 / sqrt(var + eps)
+// (torch.nn.functional.instance_norm without affine parameters or running statistics, then relu)
+// ------------------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(NR_THREADS, 2)
+vq_norm_relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ z, float2* __restrict__ stats, long long planes,
+                        long long HW, long long seg, int S, float eps) {
+  __shared__ double slot[2];
+  __shared__ double warp_part[2 * NR_WARPS];
+  const int rank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const long long cluster_id = blockIdx.x / S, nclusters = gridDim.x / S;
+  const long long s0 = (long long)rank * seg;
+  const long long s1 = s0 + seg < HW ? s0 + seg : HW;        // my segment [s0, s1) of every plane (may be empty)
+  for (long long plane = cluster_id; plane < planes; plane += nclusters) {
+    const float* xp = x + plane * HW;
+    float* zp = z + plane * HW;
+    const float shift = __ldg(xp);                           // any sample of the plane: keeps the sums well conditioned
+    float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+    if (VEC) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      const long long i0 = s0 >> 2, i1 = s1 >> 2;
+      long long i = i0 + threadIdx.x;
+      for (; i + 3 * NR_THREADS < i1; i += 4 * NR_THREADS) {   // four independent 16-byte loads per thread in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(x4 + i + u * NR_THREADS);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float dx = v[u].x - shift, dy = v[u].y - shift, dz = v[u].z - shift, dw = v[u].w - shift;
+          a0 += dx + dy; a1 += dz + dw;
+          q0 = __fmaf_rn(dx, dx, q0); q0 = __fmaf_rn(dy, dy, q0);
+          q1 = __fmaf_rn(dz, dz, q1); q1 = __fmaf_rn(dw, dw, q1);
+        }
+      }
+      for (; i < i1; i += NR_THREADS) {
+        const float4 v = __ldg(x4 + i);
+        const float dx = v.x - shift, dy = v.y - shift, dz = v.z - shift, dw = v.w - shift;
+        a0 += dx + dy; a1 += dz + dw;
+        q0 = __fmaf_rn(dx, dx, q0); q0 = __fmaf_rn(dy, dy, q0);
+        q1 = __fmaf_rn(dz, dz, q1); q1 = __fmaf_rn(dw, dw, q1);
+      }
+    } else {
+      for (long long i = s0 + threadIdx.x; i < s1; i += NR_THREADS) {
+        const float d = __ldg(xp + i) - shift;
+        a0 += d;
+        q0 = __fmaf_rn(d, d, q0);
+      }
+    }
+    double v2[2] = {(double)a0 + (double)a1, (double)q0 + (double)q1};
+    cluster_sum2(v2, slot, warp_part, S);
+    const double n = (double)HW;
+    const double md = v2[0] / n;                              // mean - shift
+    double var = v2[1] / n - md * md;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)((double)shift + md);
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rank == 0 && threadIdx.x == 0 && stats) stats[plane] = make_float2(mean, rstd);
+    if (VEC) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      float4* z4 = reinterpret_cast<float4*>(zp);
+      const long long i0 = s0 >> 2, i1 = s1 >> 2;
+      long long i = i0 + threadIdx.x;
+      for (; i + 3 * NR_THREADS < i1; i += 4 * NR_THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x4 + i + u * NR_THREADS);     // L2 hit; last use of the line
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 o;
+          o.x = fmaxf((v[u].x - mean) * rstd, 0.f); o.y = fmaxf((v[u].y - mean) * rstd, 0.f);
+          o.z = fmaxf((v[u].z - mean) * rstd, 0.f); o.w = fmaxf((v[u].w - mean) * rstd, 0.f);
+          z4[i + u * NR_THREADS] = o;                         // plain store: the quantiser reads z next
+        }
+      }
+      for (; i < i1; i += NR_THREADS) {
+        const float4 v = ldg_stream(x4 + i);
+        float4 o;
+        o.x = fmaxf((v.x - mean) * rstd, 0.f); o.y = fmaxf((v.y - mean) * rstd, 0.f);
+        o.z = fmaxf((v.z - mean) * rstd, 0.f); o.w = fmaxf((v.w - mean) * rstd, 0.f);
+        z4[i] = o;
+      }
+    } else {
+      for (long long i = s0 + threadIdx.x; i < s1; i += NR_THREADS) zp[i] = fmaxf((__ldg(xp + i) - mean) * rstd, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward: g_y = g_z where xhat > 0 else 0 (relu), g_x = rstd * (g_y - mean(g_y) - xhat * mean(g_y * xhat))
+// xhat is recomputed from x with the forward's own expression, so the relu mask is the forward's
+// ------------------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(NR_THREADS, 2)
+vq_norm_relu_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__ x, const float2* __restrict__ stats,
+                        float* __restrict__ g_x, long long planes, long long HW, long long seg, int S) {
+  __shared__ double slot[2];
+  __shared__ double warp_part[2 * NR_WARPS];
+  const int rank = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const long long cluster_id = blockIdx.x / S, nclusters = gridDim.x / S;
+  const long long s0 = (long long)rank * seg;
+  const long long s1 = s0 + seg < HW ? s0 + seg : HW;
+  for (long long plane = cluster_id; plane < planes; plane += nclusters) {
+    const float* xp = x + plane * HW;
+    const float* gp = g_z + plane * HW;
+    float* op = g_x + plane * HW;
+    const float2 st = __ldg(stats + plane);
+    const float mean = st.x, rstd = st.y;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#define NR_ACC(xv, gv, A, Bq)                                       \
+    {                                                               \
+      const float xh = ((xv) - mean) * rstd;                        \
+      const float gy = xh > 0.f ? (gv) : 0.f;                       \
+      A += gy;                                                      \
+      Bq = __fmaf_rn(gy, xh, Bq);                                   \
+    }
+    if (VEC) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      const float4* g4 = reinterpret_cast<const float4*>(gp);
+      const long long i0 = s0 >> 2, i1 = s1 >> 2;
+      long long i = i0 + threadIdx.x;
+      for (; i + NR_THREADS < i1; i += 2 * NR_THREADS) {       // four independent 16-byte loads per thread in flight
+        const float4 xa = __ldg(x4 + i), xb = __ldg(x4 + i + NR_THREADS);
+        const float4 ga = __ldg(g4 + i), gb = __ldg(g4 + i + NR_THREADS);
+        NR_ACC(xa.x, ga.x, a0, b0) NR_ACC(xa.y, ga.y, a1, b1) NR_ACC(xa.z, ga.z, a0, b0) NR_ACC(xa.w, ga.w, a1, b1)
+        NR_ACC(xb.x, gb.x, a0, b0) NR_ACC(xb.y, gb.y, a1, b1) NR_ACC(xb.z, gb.z, a0, b0) NR_ACC(xb.w, gb.w, a1, b1)
+      }
+      for (; i < i1; i += NR_THREADS) {
+        const float4 xa = __ldg(x4 + i), ga = __ldg(g4 + i);
+        NR_ACC(xa.x, ga.x, a0, b0) NR_ACC(xa.y, ga.y, a1, b1) NR_ACC(xa.z, ga.z, a0, b0) NR_ACC(xa.w, ga.w, a1, b1)
+      }
+    } else {
+      for (long long i = s0 + threadIdx.x; i < s1; i += NR_THREADS) NR_ACC(__ldg(xp + i), __ldg(gp + i), a0, b0)
+    }
+#undef NR_ACC
+    double v2[2] = {(double)a0 + (double)a1, (double)b0 + (double)b1};
+    cluster_sum2(v2, slot, warp_part, S);
+    const float m1 = (float)(v2[0] / (double)HW), m2 = (float)(v2[1] / (double)HW);
+#define NR_OUT(xv, gv) nr_gx((xv), (gv), mean, rstd, m1, m2)
+    if (VEC) {
+      const float4* x4 = reinterpret_cast<const float4*>(xp);
+      const float4* g4 = reinterpret_cast<const float4*>(gp);
+      float4* o4 = reinterpret_cast<float4*>(op);
+      const long long i0 = s0 >> 2, i1 = s1 >> 2;
+      long long i = i0 + threadIdx.x;
+      for (; i + NR_THREADS < i1; i += 2 * NR_THREADS) {
+        const float4 xa = ldg_stream(x4 + i), xb = ldg_stream(x4 + i + NR_THREADS);
+        const float4 ga = ldg_stream(g4 + i), gb = ldg_stream(g4 + i + NR_THREADS);
+        float4 oa, ob;
+        oa.x = NR_OUT(xa.x, ga.x); oa.y = NR_OUT(xa.y, ga.y); oa.z = NR_OUT(xa.z, ga.z); oa.w = NR_OUT(xa.w, ga.w);
+        ob.x = NR_OUT(xb.x, gb.x); ob.y = NR_OUT(xb.y, gb.y); ob.z = NR_OUT(xb.z, gb.z); ob.w = NR_OUT(xb.w, gb.w);
+        o4[i] = oa;
+        o4[i + NR_THREADS] = ob;
+      }
+      for (; i < i1; i += NR_THREADS) {
+        const float4 xa = ldg_stream(x4 + i), ga = ldg_stream(g4 + i);
+        float4 oa;
+        oa.x = NR_OUT(xa.x, ga.x); oa.y = NR_OUT(xa.y, ga.y); oa.z = NR_OUT(xa.z, ga.z); oa.w = NR_OUT(xa.w, ga.w);
+        o4[i] = oa;
+      }
+    } else {
+      for (long long i = s0 + threadIdx.x; i < s1; i += NR_THREADS) op[i] = NR_OUT(__ldg(xp + i), __ldg(gp + i));
+    }
+#undef NR_OUT
+  }
+}
+
+template <typename Kern, typename... Args>
+int launch_clustered(Kern kern, const NrPlan& p, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.clusters * p.S));
+  cfg.blockDim = dim3(NR_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launch();
+  return VQ_OK;
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+// forward streams one tensor through L2 per segment (256 KB), backward two (128 KB each): with 2 x 148 CTAs in flight
+// that is ~78 MB of the 126 MB L2
+constexpr long long NR_SEG_FWD = 65536, NR_SEG_BWD = 32768;
+
+int launch_norm_relu_fwd(const float* x, float* z, float* stats, long long planes, long long HW, float eps, cudaStream_t s) {
+  const bool vec = (HW % 4 == 0) && al16(x) && al16(z);
+  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_FWD);
+  float2* st = reinterpret_cast<float2*>(stats);
+  if (vec) return launch_clustered(vq_norm_relu_fwd_kernel<true>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
+  return launch_clustered(vq_norm_relu_fwd_kernel<false>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
+}
+
+int launch_norm_relu_bwd(const float* g_z, const float* x, const float* stats, float* g_x, long long planes, long long HW,
+                         cudaStream_t s) {
+  const bool vec = (HW % 4 == 0) && al16(x) && al16(g_z) && al16(g_x);
+  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_BWD);
+  const float2* st = reinterpret_cast<const float2*>(stats);
+  if (vec) return launch_clustered(vq_norm_relu_bwd_kernel<true>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);
+  return launch_clustered(vq_norm_relu_bwd_kernel<false>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);
+}
+
+}  // namespace vqb200

@@ -1,7 +1,9 @@
 """k-means codebook initialisation and the one-hot code map.
 CPU: the oracles (one-hot pinned to the unmodified reference class through tests/golden/onehot_*.npz; k-means is a
-restatement of the absent kmeans-pytorch 0.3.0 -- parity unpinned -- checked against a plain numpy Lloyd loop).
-GPU: the CUDA paths against the oracles."""
+restatement of the absent kmeans-pytorch 0.3.0, pinned to an independent implementation of the same algorithm --
+scikit-learn's Lloyd iterations from identical initial centres, tests/golden/kmeans_*.npz from
+oracle/make_golden_kmeans.py -- and checked against a plain numpy Lloyd loop).
+GPU: the CUDA paths against the oracles and against the scikit-learn golden vectors."""
 import glob
 import os
 
@@ -14,6 +16,7 @@ from oracle.onehot_oracle import onehot_oracle
 from util import ROOT
 
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "onehot_*.npz")))
+KM_GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "kmeans_*.npz")))
 DEV = "cuda:0"
 
 
@@ -47,6 +50,43 @@ def test_kmeans_oracle_is_lloyd():
     assert np.array_equal(a, ids.numpy())
     assert np.abs(cc - c.double().numpy()).max() < 1e-5
     assert it >= 2
+
+
+def test_kmeans_golden_present():
+    assert len(KM_GOLDEN) == 4
+
+
+@pytest.mark.parametrize("path", KM_GOLDEN, ids=[os.path.basename(p)[:-4] for p in KM_GOLDEN])
+def test_kmeans_oracle_matches_sklearn_golden(path):
+    """The restatement of kmeans-pytorch against scikit-learn's Lloyd iterations (independent code, float64): centres after
+    every iteration <= 1e-5 relative (max norm), the stopping rule fires at the recorded iteration, labels equal."""
+    d = np.load(path)
+    X, c0, iters = torch.from_numpy(d["X"]), torch.from_numpy(d["c0"]), int(d["iters"])
+    K = c0.shape[0]
+    for i in range(1, iters + 1):
+        _, c, it = kmeans_oracle(X, K, centers=c0, iter_limit=i)
+        ref = d["centers_per_iter"][i - 1]
+        assert it == i
+        assert np.abs(c.double().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), (i, path)
+    ids, c, it = kmeans_oracle(X, K, centers=c0)
+    assert it == iters
+    # scikit-learn's labels refer to the final centres; the package's (and the oracle's) to the centres before the last
+    # update -- assign once more with the final centres to compare like with like
+    lab = torch.cdist(X.double(), c.double()).argmin(1).numpy()
+    assert (lab != d["labels_final"]).sum() == 0
+
+
+def test_kmeans_oracle_matches_live_sklearn():
+    """Same pin, live (scikit-learn is in the image): a case that is not in the fixtures."""
+    sk = pytest.importorskip("sklearn.cluster")
+    import warnings
+    X, centres = _blobs(2500, 6, 5, 21, spread=0.8)
+    c0 = initial_centers(X, 5, seed=2)
+    _, c, it = kmeans_oracle(X, 5, centers=c0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        km = sk.KMeans(n_clusters=5, init=c0.double().numpy(), n_init=1, algorithm="lloyd", tol=0.0, max_iter=it).fit(X.double().numpy())
+    assert it >= 3 and np.abs(km.cluster_centers_ - c.double().numpy()).max() <= 1e-5 * max(1.0, np.abs(km.cluster_centers_).max())
 
 
 def test_kmeans_oracle_recovers_separated_blobs():
@@ -99,6 +139,30 @@ def test_kmeans_cuda_matches_oracle(n, d, k):
     assert not ids.is_cuda and not c.is_cuda                                     # the package returns CPU tensors
     assert torch.equal(ids, ids_ref)
     assert (c - c_ref).abs().max() <= 1e-4 * max(1.0, float(c_ref.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", KM_GOLDEN, ids=[os.path.basename(p)[:-4] for p in KM_GOLDEN])
+def test_kmeans_cuda_matches_sklearn_golden(path):
+    """The CUDA Lloyd loop against scikit-learn's centres (independent pin of the algorithm): same initial centres, same
+    number of iterations (the package's stopping rule), centres <= 1e-4 relative (max norm; fp32 sums against float64),
+    labels with respect to the final centres equal except points whose two best distances tie to 1e-5."""
+    from medical_image_editing_b200.src.functions import kmeans
+    d = np.load(path)
+    X, c0, iters = torch.from_numpy(d["X"]), torch.from_numpy(d["c0"]), int(d["iters"])
+    K = c0.shape[0]
+    ref = d["centers_per_iter"]
+    ids, c = kmeans(X.to(DEV), K, cluster_centers=c0, iter_limit=1)
+    assert np.abs(c.double().numpy() - ref[0]).max() <= 1e-4 * max(1.0, np.abs(ref[0]).max())
+    ids, c = kmeans(X.to(DEV), K, cluster_centers=c0)
+    assert np.abs(c.double().numpy() - ref[-1]).max() <= 1e-4 * max(1.0, np.abs(ref[-1]).max()), path
+    dist = torch.cdist(X.double(), torch.from_numpy(ref[-1]))
+    lab = torch.cdist(X.double(), c.double()).argmin(1).numpy()
+    bad = np.nonzero(lab != d["labels_final"])[0]
+    top2 = dist.topk(2, dim=1, largest=False).values
+    margin = (top2[:, 1] - top2[:, 0]).numpy()
+    assert all(margin[i] <= 1e-5 * max(1.0, float(top2[i, 1])) for i in bad), (len(bad), path)
+    print(f"[kmeans golden] {os.path.basename(path)}: {iters} iterations, {len(bad)} tie rows")
 
 
 @pytest.mark.gpu

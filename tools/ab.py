@@ -16,6 +16,8 @@ dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(1)
 L = pkg.lib()
 m = pkg.VQ(emb_dim=D, dict_size=K, momentum=0.99, eps=1e-5, knn_backend="torch").to(dev)
+if os.environ.get("ABSIMT") == "1":       # force the fp32 CUDA-core search
+    m.kernel_flags = 1
 N = B * H * H
 with torch.no_grad():
     cs = torch.rand(K, generator=torch.Generator().manual_seed(1234)) * (N / K) + 1.0

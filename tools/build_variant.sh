@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../medical_image_editing_b200/csrc"
 out=../../build_variants
 mkdir -p $out/obj_$name
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
-for s in vq_kernels.cu vq_assign_tc.cu vq_assign_small.cu vq_embed_loss.cu vq_capi.cu; do
+for s in vq_kernels.cu vq_assign_tc.cu vq_assign_small.cu vq_embed_loss.cu vq_norm_relu.cu vq_capi.cu; do
   nvcc $FLAGS "$@" -c $s -o $out/obj_$name/${s%.cu}.o &
 done
 wait
