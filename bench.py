@@ -992,7 +992,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cold", action="store_true", help="start from the first-step EMA state (cluster_size = 0)")
     ap.add_argument("--inline-exchange", action="store_true", help="N > 1: all-reduce + EMA update on the compute stream")
-    ap.add_argument("--fused-norm", default="none", choices=["none", "tail", "all"],
+    ap.add_argument("--fused-norm", default="all", choices=["none", "tail", "all"],
                     help="VQ-W-Net legs: InstanceNorm2d + ReLU pairs run by vq_norm_relu_fwd/bwd (tail = the quantiser's producer)")
     ap.add_argument("--no-graphs", action="store_true", help="eager step loop in the timed region instead of CUDA-graph replay")
     args = ap.parse_args()

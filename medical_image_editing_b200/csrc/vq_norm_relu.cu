@@ -23,7 +23,9 @@ namespace {
 
 constexpr int NR_THREADS = 512;
 constexpr int NR_WARPS = NR_THREADS / 32;
-constexpr int NR_MAX_CLUSTER = 8;
+constexpr int NR_NSIZES = 5;                // cluster sizes 1, 2, 4, 8, 16 (8 is the portable limit; 16 needs the non-portable attribute)
+
+struct NrCaps { int active[NR_NSIZES]; };   // co-resident clusters of size 1 << i on this device (0: size not available)
 
 struct NrPlan {
   int S;            // cluster size = segments per plane
@@ -31,17 +33,27 @@ struct NrPlan {
   int clusters;     // persistent clusters in the grid
 };
 
-// Segments of at most `seg_max` floats, so that (CTAs in flight) x (bytes a CTA streams per plane) stays below L2.
-NrPlan nr_plan(long long planes, long long HW, bool vec, long long seg_max) {
+// Segments of at most `seg_max` floats, so that (CTAs in flight) x (bytes a CTA streams per plane) stays below L2; among
+// the cluster sizes that satisfy it, the one whose persistent schedule has the shortest tail (rounds x segment length).
+// The persistent grid never holds more clusters than can be co-resident (a waiting cluster would be a second wave).
+NrPlan nr_plan(long long planes, long long HW, bool vec, long long seg_max, const NrCaps& caps) {
+  int i_min = 0;
+  while (i_min + 1 < NR_NSIZES && caps.active[i_min + 1] > 0 && (HW + (1 << i_min) - 1) / (1 << i_min) > seg_max) ++i_min;
+  int best = i_min;
+  double best_cost = 1e300;
+  for (int i = i_min; i < NR_NSIZES && caps.active[i] > 0; ++i) {
+    const int S = 1 << i;
+    const long long clusters = caps.active[i];
+    const long long rounds = (planes + clusters - 1) / clusters;
+    const double cost = (double)rounds / (double)S * (1.0 + 0.01 * S);      // mild preference for smaller clusters
+    if (cost < best_cost) { best_cost = cost; best = i; }
+  }
   NrPlan p;
-  p.S = 1;
-  while (p.S < NR_MAX_CLUSTER && (HW + p.S - 1) / p.S > seg_max) p.S <<= 1;
+  p.S = 1 << best;
   long long seg = (HW + p.S - 1) / p.S;
   if (vec) seg = (seg + 3) / 4 * 4;
   p.seg = seg;
-  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-  long long ctas = 2LL * sms;                               // two CTAs of 512 threads per SM
-  long long clusters = ctas / p.S;
+  long long clusters = caps.active[best];
   if (clusters > planes) clusters = planes;
   if (clusters < 1) clusters = 1;
   p.clusters = (int)clusters;
@@ -238,20 +250,55 @@ vq_norm_relu_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__
         float4 oa, ob;
         oa.x = NR_OUT(xa.x, ga.x); oa.y = NR_OUT(xa.y, ga.y); oa.z = NR_OUT(xa.z, ga.z); oa.w = NR_OUT(xa.w, ga.w);
         ob.x = NR_OUT(xb.x, gb.x); ob.y = NR_OUT(xb.y, gb.y); ob.z = NR_OUT(xb.z, gb.z); ob.w = NR_OUT(xb.w, gb.w);
-        o4[i] = oa;
-        o4[i + NR_THREADS] = ob;
+        __stcs(o4 + i, oa);                                    // evict-first: g_x must not push the lines pass 2 still needs out of L2
+        __stcs(o4 + i + NR_THREADS, ob);
       }
       for (; i < i1; i += NR_THREADS) {
         const float4 xa = ldg_stream(x4 + i), ga = ldg_stream(g4 + i);
         float4 oa;
         oa.x = NR_OUT(xa.x, ga.x); oa.y = NR_OUT(xa.y, ga.y); oa.z = NR_OUT(xa.z, ga.z); oa.w = NR_OUT(xa.w, ga.w);
-        o4[i] = oa;
+        __stcs(o4 + i, oa);
       }
     } else {
       for (long long i = s0 + threadIdx.x; i < s1; i += NR_THREADS) op[i] = NR_OUT(__ldg(xp + i), __ldg(gp + i));
     }
 #undef NR_OUT
   }
+}
+
+// how many clusters of each size can be co-resident (two CTAs of 512 threads per SM at best), per kernel and device
+template <typename Kern>
+const NrCaps& cluster_caps(Kern kern, int slot) {
+  static NrCaps cached[kMaxDevices][4];
+  static bool have[kMaxDevices][4] = {};
+  const int dev = current_device();
+  if (have[dev][slot]) return cached[dev][slot];
+  NrCaps c{};
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+  const bool big = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  for (int i = 0; i < NR_NSIZES; ++i) {
+    const int S = 1 << i;
+    if (S > 8 && !big) break;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * sms / S * S));
+    cfg.blockDim = dim3(NR_THREADS);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+      if (S == 1) n = 2 * sms;                              // plain CTAs: the launch bounds guarantee two per SM
+      else break;
+    }
+    if (n > 2 * sms / S) n = 2 * sms / S;
+    c.active[i] = n;
+  }
+  (void)cudaGetLastError();
+  cached[dev][slot] = c;
+  have[dev][slot] = true;
+  return cached[dev][slot];
 }
 
 template <typename Kern, typename... Args>
@@ -275,24 +322,31 @@ inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
-// forward streams one tensor through L2 per segment (256 KB), backward two (128 KB each): with 2 x 148 CTAs in flight
-// that is ~78 MB of the 126 MB L2
-constexpr long long NR_SEG_FWD = 65536, NR_SEG_BWD = 32768;
+// L2 budget: with 2 x 148 CTAs in flight, a forward segment of 128 KB keeps 38 MB of x (re-read by pass 2) plus as much
+// freshly written z in the 126 MB L2; a backward segment of 64 KB keeps 2 x 19 MB of x / g_z plus 19 MB of g_x.
+// (256 KB / 128 KB segments measured 71 % of the HBM peak at 256^2 planes but 54-57 % at 512^2: the re-read missed.)
+constexpr long long NR_SEG_FWD = 32768, NR_SEG_BWD = 16384;
 
 int launch_norm_relu_fwd(const float* x, float* z, float* stats, long long planes, long long HW, float eps, cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(z);
-  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_FWD);
   float2* st = reinterpret_cast<float2*>(stats);
-  if (vec) return launch_clustered(vq_norm_relu_fwd_kernel<true>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
+  if (vec) {
+    const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_FWD, cluster_caps(vq_norm_relu_fwd_kernel<true>, 0));
+    return launch_clustered(vq_norm_relu_fwd_kernel<true>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
+  }
+  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_FWD, cluster_caps(vq_norm_relu_fwd_kernel<false>, 1));
   return launch_clustered(vq_norm_relu_fwd_kernel<false>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
 }
 
 int launch_norm_relu_bwd(const float* g_z, const float* x, const float* stats, float* g_x, long long planes, long long HW,
                          cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(g_z) && al16(g_x);
-  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_BWD);
   const float2* st = reinterpret_cast<const float2*>(stats);
-  if (vec) return launch_clustered(vq_norm_relu_bwd_kernel<true>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);
+  if (vec) {
+    const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_BWD, cluster_caps(vq_norm_relu_bwd_kernel<true>, 2));
+    return launch_clustered(vq_norm_relu_bwd_kernel<true>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);
+  }
+  const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_BWD, cluster_caps(vq_norm_relu_bwd_kernel<false>, 3));
   return launch_clustered(vq_norm_relu_bwd_kernel<false>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);
 }
 

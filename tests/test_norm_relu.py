@@ -80,18 +80,27 @@ def test_norm_relu_cuda_matches_oracle(shape, mean, std):
     g_z = _x(shape, 8)
     ref = norm_relu_oracle(x)
     ref_g = norm_relu_oracle_grad(x.double(), g_z.double()).float()       # float64 autograd: the tighter reference
+    # An element whose normalised value is within rounding of 0 may fall on either side of the relu in two correct fp32
+    # implementations (its gradient is then g_z * rstd or 0): such elements are excluded from the gradient comparison;
+    # their effect on the plane means (1 / HW of one element) stays inside the tolerance.
+    safe = torch.nn.functional.instance_norm(x.double()).abs() > 1e-5
+
+    def grad_err(a, b, m):
+        return float(((a.double() - b.double()).abs() * m).max() / b.double().abs().max().clamp_min(1e-30))
+
     xd = x.to(DEV).requires_grad_(True)
     z = instance_norm_relu(xd)
     (g_x,) = torch.autograd.grad(z, xd, g_z.to(DEV))
     assert z.shape == x.shape and z.is_contiguous()
     assert rel_err(z.cpu(), ref) <= 1e-5                                   # max |a - b| / max |b|
-    assert bool(((z.cpu() > 0) == (ref > 0)).float().mean() > 0.99999)     # relu mask: only exact-zero crossings may flip
-    assert rel_err(g_x.cpu(), ref_g) <= 2e-5
+    assert bool((((z.cpu() > 0) == (ref > 0)) | ~safe).all())              # relu mask: only zero crossings may flip
+    assert grad_err(g_x.cpu(), ref_g, safe) <= 2e-5
     # against stock torch-CUDA on the same device (the path the reference takes on a GPU)
     xt = x.to(DEV).requires_grad_(True)
     zt = torch.relu(torch.nn.functional.instance_norm(xt))
     (gt,) = torch.autograd.grad(zt, xt, g_z.to(DEV))
-    assert rel_err(z, zt) <= 1e-5 and rel_err(g_x, gt) <= 2e-5
+    assert rel_err(z, zt) <= 1e-5 and grad_err(g_x, gt, safe.to(DEV)) <= 2e-5
+    print(f"[norm_relu] {shape}: {int((~safe).sum())} elements within 1e-5 of the relu threshold excluded")
 
 
 @pytest.mark.gpu
@@ -145,5 +154,45 @@ def test_fused_tail_inside_reference_vqwnet():
             (ga,) = torch.autograd.grad(la, xa)
             (gb,) = torch.autograd.grad(lb, xb)
             assert rel_err(gb, ga) <= 1e-3
+    finally:
+        torch.backends.cudnn.allow_tf32 = cudnn
+
+
+@pytest.mark.gpu
+def test_all_pairs_fused_in_wnet_harness_training_step():
+    """tools/wnet.py with every InstanceNorm2d + ReLU pair fused (bench.py --fused-norm all) against the stock layers:
+    one training step from identical weights -- loss, code-map agreement, parameter gradients."""
+    import copy
+    import os
+    import sys
+    import medical_image_editing_b200 as pkg
+    from medical_image_editing_b200.src.functions import InstanceNormReLU, fuse_norm_relu_pairs
+    from util import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from wnet import WNetHarness
+    torch.manual_seed(0)
+    a = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch"), 1,
+                    widths=(16, 16, 32, 32, 64), dict_size=32).to(DEV)
+    b = copy.deepcopy(a)
+    n = sum(fuse_norm_relu_pairs(m) for m in [m for m in b.modules() if isinstance(m, nn.Sequential)])
+    assert n == 36 and sum(isinstance(m, InstanceNormReLU) for m in b.modules()) == 36      # 18 conv pairs x 2
+    cudnn = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = _x((2, 1, 64, 64), 5).clamp(-1, 1).to(DEV)
+        oa, ob = a(x), b(x)
+        same = (oa["ids"] == ob["ids"]).float().mean().item()
+        assert rel_err(ob["embed"], oa["embed"]) <= 1e-4 and same >= 0.995, same
+        la = (oa["recon"] - x).pow(2).mean() + oa["commit_loss"]
+        lb = (ob["recon"] - x).pow(2).mean() + ob["commit_loss"]
+        assert abs(la.item() - lb.item()) <= 1e-3 * abs(la.item())
+        la.backward()
+        lb.backward()
+        if same == 1.0:
+            # relative to the largest gradient of the network: a convolution that feeds an InstanceNorm has a gradient of
+            # ~0 by scale invariance (1e-6 of the others), i.e. pure rounding noise in both implementations
+            gmax = max(float(p.grad.abs().max()) for p in a.parameters())
+            for (na, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+                assert float((pb.grad - pa.grad).abs().max()) <= 2e-3 * gmax, na
     finally:
         torch.backends.cudnn.allow_tf32 = cudnn
