@@ -16,13 +16,17 @@ CUDA graphs of the step; `eager` = the same loop launched from Python, `--no-gra
 `e2e` = the same through the module's public API with HOST (pinned) input and the result (loss +
 code map) read back every step; `roofline` = the dominant kernel (nearest-code search) against the
 measured HBM peak; `cpu_baseline` = the reference's own `VQModule` (git-ignored mirror baseline/_ref/src made by
-`__graft_entry__.build()`; the oracle port when no copy is reachable) on the host cores, bounded sample; `north_star` =
+`__graft_entry__.build()`; the oracle port when no copy is reachable) on the host cores, bounded sample, with
+`cpu_baseline.reference_on_gpu` = the same unmodified module under stock torch-CUDA on this GPU (sanity / noise floor:
+its step time and the number of code ids that differ from this library's in an eval forward); `north_star` =
 the K = 512, D = 256 point (eval and train, clustered / ReLU / Gaussian input) with its own roofline fractions;
 `parity_check` = TC-vs-CUDA-core ids on one buffer and, for N > 1, the all-reduced statistics against the gathered
 local ones.  `vqwnet_train` = the other half of BASELINE's metric: VQ-W-Net training slices/s
 (BASELINE config 2: batch 16 of 256x256 slices per GPU, tools/wnet.py around this repo's quantiser, stock cuDNN
 convolutions, Adam), device-resident and end-to-end, measured after the headline region; `--workload vqwnet`
 makes it the line's own metric (and `--impl reference --workload vqwnet` times the same network on the host cores).
+`--fused-norm all|tail|none` (default all): the harness's InstanceNorm2d + ReLU pairs run through vq_norm_relu_fwd/bwd
+(`tail` = only the pair that produces the quantiser's input, `none` = stock torch layers).
 """
 from __future__ import annotations
 

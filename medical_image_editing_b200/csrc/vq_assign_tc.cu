@@ -347,9 +347,12 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 //              the main kernel turns it into bound_c(|z|) = |z| * A_c + B_c  (accumulator units)
 //   meta[0] = r_cap, meta[1] = smallest norm of an excluded code as uint32 bits (0x7F800000 = none; set by prep)
 //
-// Rank by counting: every thread owns one sorted-order key (norm bits, original index) and counts the smaller keys
-// in shared memory -- O(K^2 / threads) compares, no sorting network, any number of CTAs.
+// Rank by counting: eight threads own one sorted-order key (norm bits, original index); each counts the smaller keys in
+// an eighth of the shared-memory copy, three shuffles add the counts -- O(K^2 / threads) compares, no sorting network,
+// any number of CTAs (32 codes per CTA: 16 CTAs at K = 512; one thread per code and 2 CTAs took 14 us of mostly
+// dependent shared-memory latency).
 constexpr int TC_PREP2_THREADS = 256;
+constexpr int TC_PREP2_CODES = TC_PREP2_THREADS / 8;       // codes per CTA
 __global__ void __launch_bounds__(TC_PREP2_THREADS)
 vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, int K, int D, int BN, int nb,
                    float* __restrict__ es, float* __restrict__ eaug_img, int* __restrict__ perm,
@@ -390,62 +393,75 @@ vq_tc_prep2_kernel(const float* __restrict__ E, const float* __restrict__ e2, in
   __syncthreads();
   const float rcap = s_rcap;
   const float slop = 1.f + (float)D * 1.2e-7f + 1e-5f;          // |e| was computed in fp32 from a rounded |e|^2
-  const int i = blockIdx.x * blockDim.x + tid;                 // code (i < K) or padding slot (K <= i < ktot)
-  if (i == 0) meta[0] = __float_as_uint(rcap);
-  if (i < ktot) {
-    int pos = i;                              // padding keeps its slot: K .. ktot-1
-    float a0 = -1e30f, a1 = 0.f, a2 = 0.f;    // padding / excluded codes never win
-    const bool real = i < K;
-    if (real) {
-      const uint32_t mine = keys[i];
-      int rank = 0;
-      int j = 0;
-      const uint4* k4 = reinterpret_cast<const uint4*>(keys);
-      for (; j + 4 <= K; j += 4) {            // broadcast reads, four keys per 16-byte load
-        const uint4 kk = k4[j >> 2];
-        rank += (kk.x < mine || (kk.x == mine && j < i)) ? 1 : 0;
-        rank += (kk.y < mine || (kk.y == mine && j + 1 < i)) ? 1 : 0;
-        rank += (kk.z < mine || (kk.z == mine && j + 2 < i)) ? 1 : 0;
-        rank += (kk.w < mine || (kk.w == mine && j + 3 < i)) ? 1 : 0;
-      }
-      for (; j < K; ++j) {
-        const uint32_t kj = keys[j];
-        rank += (kj < mine || (kj == mine && j < i)) ? 1 : 0;
-      }
-      pos = rank;
-      const float r = __uint_as_float(mine);
-      if (r <= rcap) {
-        // tf32 operands are TRUNCATED (tools/trunc_check.py), so every product shrinks by a factor in (1 - 2^-9, 1]:
-        // (1 + 2^-10) * dot~ is within 2^-10 sum|z_d e_d| of the exact dot -- half of the uncentred bound.  Comparing
-        // (1 + 2^-10) dot~ - |e|^2/2 is comparing dot~ - |e|^2 / (2 (1 + 2^-10)): fold the factor into the augmentation.
-        const float x = -0.5f * e2[i] * (1.0f / (1.0f + 0.0009765625f));
-        a0 = tf32_trunc(x);
-        const float r1 = x - a0;
-        a1 = tf32_trunc(r1);
-        a2 = tf32_trunc(r1 - a1);
-        atomicMax(&rmax[pos >> 5], __float_as_uint(r * slop));
-      } else {
-        atomicMin(&meta[1], __float_as_uint(r / slop));
-      }
+  // eight threads per code (TC_PREP2_CODES codes per CTA): each counts an eighth of the keys, then they share the row copy
+  const int sub = tid & 7;
+  const int i = blockIdx.x * TC_PREP2_CODES + (tid >> 3);        // code (i < K) or padding slot (K <= i < ktot)
+  if (i == 0 && sub == 0) meta[0] = __float_as_uint(rcap);
+  const bool inside = i < ktot;
+  const bool real = i < K;
+  int rank = 0;
+  uint32_t mine = 0u;
+  if (real) {
+    mine = keys[i];
+    const int per = ((K + 31) / 32) * 4;                         // keys per sub-thread, a multiple of 4
+    const int j0 = sub * per;
+    const int j1 = min(K, j0 + per);
+    int j = j0;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    for (; j + 4 <= j1; j += 4) {                                // four keys per 16-byte load
+      const uint4 kk = k4[j >> 2];
+      rank += (kk.x < mine || (kk.x == mine && j < i)) ? 1 : 0;
+      rank += (kk.y < mine || (kk.y == mine && j + 1 < i)) ? 1 : 0;
+      rank += (kk.z < mine || (kk.z == mine && j + 2 < i)) ? 1 : 0;
+      rank += (kk.w < mine || (kk.w == mine && j + 3 < i)) ? 1 : 0;
     }
-    perm[pos] = real ? i : 0;
-    const int blk = pos / BN, rr = pos % BN, grp = rr >> 3, row = rr & 7;
-    float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
-    base[0] = a0; base[1] = a1; base[2] = a2; base[3] = real ? e2[i] : 0.f;   // [3]: exact |e|^2 (times the zero row of the ones block)
-    base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
-    // sorted copy of the codebook row (TMA source)
+    for (; j < j1; ++j) {
+      const uint32_t kj = keys[j];
+      rank += (kj < mine || (kj == mine && j < i)) ? 1 : 0;
+    }
+  }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  if (inside) {
+    const int pos = real ? rank : i;          // padding keeps its slot: K .. ktot-1
+    if (sub == 0) {
+      float a0 = -1e30f, a1 = 0.f, a2 = 0.f;  // padding / excluded codes never win
+      if (real) {
+        const float r = __uint_as_float(mine);
+        if (r <= rcap) {
+          // tf32 operands are TRUNCATED (tools/trunc_check.py), so every product shrinks by a factor in (1 - 2^-9, 1]:
+          // (1 + 2^-10) * dot~ is within 2^-10 sum|z_d e_d| of the exact dot -- half of the uncentred bound.  Comparing
+          // (1 + 2^-10) dot~ - |e|^2/2 is comparing dot~ - |e|^2 / (2 (1 + 2^-10)): fold the factor into the augmentation.
+          const float x = -0.5f * e2[i] * (1.0f / (1.0f + 0.0009765625f));
+          a0 = tf32_trunc(x);
+          const float r1 = x - a0;
+          a1 = tf32_trunc(r1);
+          a2 = tf32_trunc(r1 - a1);
+          atomicMax(&rmax[pos >> 5], __float_as_uint(r * slop));
+        } else {
+          atomicMin(&meta[1], __float_as_uint(r / slop));
+        }
+      }
+      perm[pos] = real ? i : 0;
+      const int blk = pos / BN, rr = pos % BN, grp = rr >> 3, row = rr & 7;
+      float* base = eaug_img + (size_t)blk * BN * 8 + grp * 64 + row * 4;
+      base[0] = a0; base[1] = a1; base[2] = a2; base[3] = real ? e2[i] : 0.f;   // [3]: exact |e|^2 (times the zero row of the ones block)
+      base[32] = 0.f; base[33] = 0.f; base[34] = 0.f; base[35] = 0.f;
+    }
+    // sorted copy of the codebook row (TMA source): the eight threads of the code take every eighth 16-byte piece
     const int dq = D >> 2;
     float4* dst = reinterpret_cast<float4*>(es + (size_t)pos * D);
     const float4* src = reinterpret_cast<const float4*>(E + (size_t)(real ? i : 0) * D);
-    int j = 0;
-    for (; j + 8 <= dq; j += 8) {                 // eight 16-byte loads in flight per thread
-      float4 v[8];
+    int j = sub;
+    for (; j + 24 < dq; j += 32) {                // four 16-byte loads in flight per thread
+      float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = real ? __ldg(src + j + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) v[u] = real ? __ldg(src + j + 8 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dst[j + u] = v[u];
+      for (int u = 0; u < 4; ++u) dst[j + 8 * u] = v[u];
     }
-    for (; j < dq; ++j) dst[j] = real ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; j < dq; j += 8) dst[j] = real ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -2744,7 +2760,7 @@ static int launch_assign_r3(const FwdArgs& a, cudaStream_t s) {
   uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
   uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
   const int ktot = g.nb * g.BN;
-  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_CODES - 1) / TC_PREP2_CODES, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
       a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
@@ -2834,7 +2850,7 @@ int launch_assign_tc_impl(const FwdArgs& a, float* dbg, cudaStream_t s) {
   uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
   uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
   const int ktot = g.nb * g.BN;
-  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_CODES - 1) / TC_PREP2_CODES, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
       a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());
@@ -2957,7 +2973,7 @@ static int launch_assign_tcs_impl(const FwdArgs& a, float* dbg, cudaStream_t s) 
   uint32_t* meta = reinterpret_cast<uint32_t*>(a.ws.tc_meta);
   uint32_t* rmax = reinterpret_cast<uint32_t*>(a.ws.tc_ctab);
   const int ktot = g.nb * g.BN;
-  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_THREADS - 1) / TC_PREP2_THREADS, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
+  vq_tc_prep2_kernel<<<(ktot + TC_PREP2_CODES - 1) / TC_PREP2_CODES, TC_PREP2_THREADS, (size_t)a.K * 4, s>>>(
       a.embed, a.ws.e2, a.K, a.D, g.BN, g.nb, a.ws.tc_es, eaug_img, a.ws.tc_perm, rmax, meta);
   count_launch();
   VQ_CUDA_CHECK(cudaGetLastError());

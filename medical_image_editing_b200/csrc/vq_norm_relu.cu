@@ -266,6 +266,106 @@ vq_norm_relu_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// small planes (HW <= 1024, HW % 4 == 0: the 32 x 32 and 16 x 16 levels of the U-Net): one WARP per plane, the plane
+// stays in registers between the statistics and the output (single pass, no block-level synchronisation -- the
+// CTA-per-plane kernels above spend two barriers and an idle half of the CTA on a 256-element plane)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int NRS_WARPS = 8;
+constexpr int NRS_NV = 8;                    // float4 per lane: 32 lanes x 8 x 4 = 1024 floats
+constexpr long long NRS_MAX_HW = 32 * NRS_NV * 4;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * NRS_WARPS)
+vq_norm_relu_fwd_small_kernel(const float* __restrict__ x, float* __restrict__ z, float2* __restrict__ stats, long long planes,
+                              int nq /* HW / 4 */, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * NRS_WARPS + (threadIdx.x >> 5), nw = (long long)gridDim.x * NRS_WARPS;
+  for (long long plane = w0; plane < planes; plane += nw) {
+    const float4* x4 = reinterpret_cast<const float4*>(x) + plane * nq;
+    float4* z4 = reinterpret_cast<float4*>(z) + plane * nq;
+    float4 v[NRS_NV];
+#pragma unroll
+    for (int u = 0; u < NRS_NV; ++u) {
+      const int i = lane + 32 * u;
+      v[u] = i < nq ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float shift = __shfl_sync(0xffffffffu, v[0].x, 0);
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int u = 0; u < NRS_NV; ++u) {
+      if (lane + 32 * u < nq) {
+        const float dx = v[u].x - shift, dy = v[u].y - shift, dz = v[u].z - shift, dw = v[u].w - shift;
+        a += (dx + dy) + (dz + dw);
+        q = __fmaf_rn(dx, dx, q); q = __fmaf_rn(dy, dy, q); q = __fmaf_rn(dz, dz, q); q = __fmaf_rn(dw, dw, q);
+      }
+    }
+    const double n = 4.0 * (double)nq;
+    const double md = warp_sum_d((double)a) / n;
+    double var = warp_sum_d((double)q) / n - md * md;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)((double)shift + md);
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (lane == 0 && stats) stats[plane] = make_float2(mean, rstd);
+#pragma unroll
+    for (int u = 0; u < NRS_NV; ++u) {
+      const int i = lane + 32 * u;
+      if (i < nq) {
+        float4 o;
+        o.x = fmaxf((v[u].x - mean) * rstd, 0.f); o.y = fmaxf((v[u].y - mean) * rstd, 0.f);
+        o.z = fmaxf((v[u].z - mean) * rstd, 0.f); o.w = fmaxf((v[u].w - mean) * rstd, 0.f);
+        z4[i] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * NRS_WARPS)
+vq_norm_relu_bwd_small_kernel(const float* __restrict__ g_z, const float* __restrict__ x, const float2* __restrict__ stats,
+                              float* __restrict__ g_x, long long planes, int nq) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * NRS_WARPS + (threadIdx.x >> 5), nw = (long long)gridDim.x * NRS_WARPS;
+  for (long long plane = w0; plane < planes; plane += nw) {
+    const float4* x4 = reinterpret_cast<const float4*>(x) + plane * nq;
+    const float4* g4 = reinterpret_cast<const float4*>(g_z) + plane * nq;
+    float4* o4 = reinterpret_cast<float4*>(g_x) + plane * nq;
+    const float2 st = __ldg(stats + plane);
+    const float mean = st.x, rstd = st.y;
+    float4 xh[NRS_NV], gy[NRS_NV];              // normalised input and relu-masked gradient, kept for the second half
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int u = 0; u < NRS_NV; ++u) {
+      const int i = lane + 32 * u;
+      const bool in = i < nq;
+      const float4 xv = in ? __ldg(x4 + i) : make_float4(mean, mean, mean, mean);
+      const float4 gv = in ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[u].x = (xv.x - mean) * rstd; xh[u].y = (xv.y - mean) * rstd; xh[u].z = (xv.z - mean) * rstd; xh[u].w = (xv.w - mean) * rstd;
+      gy[u].x = xh[u].x > 0.f ? gv.x : 0.f; gy[u].y = xh[u].y > 0.f ? gv.y : 0.f;
+      gy[u].z = xh[u].z > 0.f ? gv.z : 0.f; gy[u].w = xh[u].w > 0.f ? gv.w : 0.f;
+      a += (gy[u].x + gy[u].y) + (gy[u].z + gy[u].w);
+      b = __fmaf_rn(gy[u].x, xh[u].x, b); b = __fmaf_rn(gy[u].y, xh[u].y, b);
+      b = __fmaf_rn(gy[u].z, xh[u].z, b); b = __fmaf_rn(gy[u].w, xh[u].w, b);
+    }
+    const double n = 4.0 * (double)nq;
+    const float m1 = (float)(warp_sum_d((double)a) / n), m2 = (float)(warp_sum_d((double)b) / n);
+#pragma unroll
+    for (int u = 0; u < NRS_NV; ++u) {
+      const int i = lane + 32 * u;
+      if (i < nq) {
+        float4 o;
+        o.x = rstd * ((gy[u].x - m1) - xh[u].x * m2); o.y = rstd * ((gy[u].y - m1) - xh[u].y * m2);
+        o.z = rstd * ((gy[u].z - m1) - xh[u].z * m2); o.w = rstd * ((gy[u].w - m1) - xh[u].w * m2);
+        o4[i] = o;
+      }
+    }
+  }
+}
+
 // how many clusters of each size can be co-resident (two CTAs of 512 threads per SM at best), per kernel and device
 template <typename Kern>
 const NrCaps& cluster_caps(Kern kern, int slot) {
@@ -330,6 +430,15 @@ constexpr long long NR_SEG_FWD = 32768, NR_SEG_BWD = 16384;
 int launch_norm_relu_fwd(const float* x, float* z, float* stats, long long planes, long long HW, float eps, cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(z);
   float2* st = reinterpret_cast<float2*>(stats);
+  if (vec && HW <= NRS_MAX_HW) {
+    const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+    long long blocks = (planes + NRS_WARPS - 1) / NRS_WARPS;
+    if (blocks > 8LL * sms) blocks = 8LL * sms;
+    vq_norm_relu_fwd_small_kernel<<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(x, z, st, planes, (int)(HW / 4), eps);
+    count_launch();
+    VQ_CUDA_CHECK(cudaGetLastError());
+    return VQ_OK;
+  }
   if (vec) {
     const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_FWD, cluster_caps(vq_norm_relu_fwd_kernel<true>, 0));
     return launch_clustered(vq_norm_relu_fwd_kernel<true>, p, s, x, z, st, planes, HW, p.seg, p.S, eps);
@@ -342,6 +451,15 @@ int launch_norm_relu_bwd(const float* g_z, const float* x, const float* stats, f
                          cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(g_z) && al16(g_x);
   const float2* st = reinterpret_cast<const float2*>(stats);
+  if (vec && HW <= NRS_MAX_HW) {
+    const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+    long long blocks = (planes + NRS_WARPS - 1) / NRS_WARPS;
+    if (blocks > 8LL * sms) blocks = 8LL * sms;
+    vq_norm_relu_bwd_small_kernel<<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(g_z, x, st, g_x, planes, (int)(HW / 4));
+    count_launch();
+    VQ_CUDA_CHECK(cudaGetLastError());
+    return VQ_OK;
+  }
   if (vec) {
     const NrPlan p = nr_plan(planes, HW, vec, NR_SEG_BWD, cluster_caps(vq_norm_relu_bwd_kernel<true>, 2));
     return launch_clustered(vq_norm_relu_bwd_kernel<true>, p, s, g_z, x, st, g_x, planes, HW, p.seg, p.S);

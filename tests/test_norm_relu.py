@@ -64,7 +64,8 @@ def test_fuse_vq_tail_on_reference_vqwnet_structure():
 
 
 # ----------------------------------------------------------------------------------------------- GPU
-SHAPES = [((2, 8, 16, 16), 0.0, 1.0), ((3, 5, 7, 9), 0.5, 2.0),            # HW % 4 != 0: scalar path
+SHAPES = [((2, 8, 16, 16), 0.0, 1.0), ((3, 5, 7, 9), 0.5, 2.0),            # warp-per-plane path; HW % 4 != 0: scalar path
+          ((2, 16, 32, 32), 0.3, 1.5), ((1, 3, 2, 514), 0.0, 1.0),         # largest warp-per-plane plane; just above it
           ((1, 64, 256, 256), 0.2, 1.0),                                   # config-2 planes: one CTA per plane
           ((2, 3, 512, 512), -1.0, 0.5),                                   # clusters of 4 (forward) / 8 (backward)
           ((1, 2, 1024, 1024), 0.0, 1.0),                                  # segments larger than the L2 budget
