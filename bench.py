@@ -710,7 +710,11 @@ def run_b200_arm(args, wl, wl_name):
                     "h2d_bytes_per_step": z_host[0].numel() * 4, "d2h_bytes_per_step": ids_host.numel() * 8 + 4,
                     "returned": "code map (int64) + loss; quantized and the input gradient stay on the device",
                     "overlap": "step i+1 H2D (copy stream, double buffer) overlaps step i kernels; result read every step",
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "h2d_GBps_per_gpu": z_host[0].numel() * 4 / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                    "h2d_ceiling": "measured on this pool's 8-GPU box (profiles/r02_h2d_concurrent_8gpu.json, tools/h2d_concurrent.py): "
+                                   "55.5 GB/s per GPU copying alone, 23.7 (GPUs 0-3) / 35.9 (GPUs 4-7) GB/s per GPU with all eight "
+                                   "copying at once (238 GB/s in total): the N = 8 e2e figure is bound by the host's PCIe fabric"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
