@@ -267,13 +267,14 @@ vq_norm_relu_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// small planes (HW <= 1024, HW % 4 == 0: the 32 x 32 and 16 x 16 levels of the U-Net): one WARP per plane, the plane
+// small planes (HW <= 4096 forward / 1024 backward, HW % 4 == 0: the deep levels of the U-Net): one WARP per plane, the plane
 // stays in registers between the statistics and the output (single pass, no block-level synchronisation -- the
 // CTA-per-plane kernels above spend two barriers and an idle half of the CTA on a 256-element plane)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int NRS_WARPS = 8;
-constexpr int NRS_NV = 8;                    // float4 per lane: 32 lanes x 8 x 4 = 1024 floats
-constexpr long long NRS_MAX_HW = 32 * NRS_NV * 4;
+// float4 per lane (template parameter NV): 2 -> planes of <= 256 floats, 8 -> <= 1024, 32 -> <= 4096 (forward only: the
+// backward keeps two values per element)
+constexpr long long NRS_MAX_HW_FWD = 32 * 32 * 4, NRS_MAX_HW_BWD = 32 * 8 * 4;
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -281,6 +282,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+template <int NRS_NV>
 __global__ void __launch_bounds__(32 * NRS_WARPS)
 vq_norm_relu_fwd_small_kernel(const float* __restrict__ x, float* __restrict__ z, float2* __restrict__ stats, long long planes,
                               int nq /* HW / 4 */, float eps) {
@@ -325,6 +327,7 @@ vq_norm_relu_fwd_small_kernel(const float* __restrict__ x, float* __restrict__ z
   }
 }
 
+template <int NRS_NV>
 __global__ void __launch_bounds__(32 * NRS_WARPS)
 vq_norm_relu_bwd_small_kernel(const float* __restrict__ g_z, const float* __restrict__ x, const float2* __restrict__ stats,
                               float* __restrict__ g_x, long long planes, int nq) {
@@ -430,11 +433,14 @@ constexpr long long NR_SEG_FWD = 32768, NR_SEG_BWD = 16384;
 int launch_norm_relu_fwd(const float* x, float* z, float* stats, long long planes, long long HW, float eps, cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(z);
   float2* st = reinterpret_cast<float2*>(stats);
-  if (vec && HW <= NRS_MAX_HW) {
+  if (vec && HW <= NRS_MAX_HW_FWD) {
     const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
     long long blocks = (planes + NRS_WARPS - 1) / NRS_WARPS;
     if (blocks > 8LL * sms) blocks = 8LL * sms;
-    vq_norm_relu_fwd_small_kernel<<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(x, z, st, planes, (int)(HW / 4), eps);
+    const int nq = (int)(HW / 4);
+    if (nq <= 64) vq_norm_relu_fwd_small_kernel<2><<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(x, z, st, planes, nq, eps);
+    else if (nq <= 256) vq_norm_relu_fwd_small_kernel<8><<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(x, z, st, planes, nq, eps);
+    else vq_norm_relu_fwd_small_kernel<32><<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(x, z, st, planes, nq, eps);
     count_launch();
     VQ_CUDA_CHECK(cudaGetLastError());
     return VQ_OK;
@@ -451,11 +457,13 @@ int launch_norm_relu_bwd(const float* g_z, const float* x, const float* stats, f
                          cudaStream_t s) {
   const bool vec = (HW % 4 == 0) && al16(x) && al16(g_z) && al16(g_x);
   const float2* st = reinterpret_cast<const float2*>(stats);
-  if (vec && HW <= NRS_MAX_HW) {
+  if (vec && HW <= NRS_MAX_HW_BWD) {
     const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
     long long blocks = (planes + NRS_WARPS - 1) / NRS_WARPS;
     if (blocks > 8LL * sms) blocks = 8LL * sms;
-    vq_norm_relu_bwd_small_kernel<<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(g_z, x, st, g_x, planes, (int)(HW / 4));
+    const int nq = (int)(HW / 4);
+    if (nq <= 64) vq_norm_relu_bwd_small_kernel<2><<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(g_z, x, st, g_x, planes, nq);
+    else vq_norm_relu_bwd_small_kernel<8><<<(unsigned)blocks, 32 * NRS_WARPS, 0, s>>>(g_z, x, st, g_x, planes, nq);
     count_launch();
     VQ_CUDA_CHECK(cudaGetLastError());
     return VQ_OK;
