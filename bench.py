@@ -789,6 +789,9 @@ def fuse_wnet_norms(model, mode):
     return 0
 
 
+CUDNN_BENCHMARK = int(os.environ.get("VQ_BENCH_CUDNN_BENCHMARK", "0"))
+
+
 def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, name="vqwnet", fused_norm="none"):
     """VQ-W-Net train slices/s on this rank's GPU (data parallel over `world` ranks).  Returns a dict on rank 0."""
     import torch.distributed as dist
@@ -799,6 +802,9 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, na
 
     L = pkg.lib()
     B, H, micro = wnet_shape(name, world)
+    # the convolutions around the quantiser are stock cuDNN (out of scope); the only knob the harness
+    # touches is cuDNN's own algorithm search (same fp32 / TF32 arithmetic, the fastest algorithm per shape)
+    torch.backends.cudnn.benchmark = bool(CUDNN_BENCHMARK)
     torch.manual_seed(0)
     model = WNetHarness(lambda d, k: pkg.VQ(emb_dim=d, dict_size=k, momentum=0.99, eps=1e-5, knn_backend="torch",
                                             reduce_mode="sum", overlap_exchange=(world > 1 and not inline_exchange)),
@@ -870,7 +876,7 @@ def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, na
                                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel": "vq_assign_tc",
                                             "peak_source": f"MEASURED_PEAKS.json ({which})"}),
         "replicas_in_sync": bool(in_sync), "final_loss": losses[-1] if losses else None,
-        "fused_norm": fused_norm, "fused_norm_pairs": n_fused,
+        "fused_norm": fused_norm, "fused_norm_pairs": n_fused, "cudnn_benchmark": bool(CUDNN_BENCHMARK),
     }
 
 
@@ -981,7 +987,8 @@ def run_wnet_b200_arm(args):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wnet_config(world, name=args.workload),
                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks, "roofline": r["roofline"],
                "cpu_baseline": cpu, "replicas_in_sync": r["replicas_in_sync"], "final_loss": r["final_loss"],
-               "fused_norm": r["fused_norm"], "fused_norm_pairs": r["fused_norm_pairs"]}
+               "fused_norm": r["fused_norm"], "fused_norm_pairs": r["fused_norm_pairs"],
+               "cudnn_benchmark": r["cudnn_benchmark"]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1003,7 +1010,10 @@ def main():
     ap.add_argument("--fused-norm", default="all", choices=["none", "tail", "all"],
                     help="VQ-W-Net legs: InstanceNorm2d + ReLU pairs run by vq_norm_relu_fwd/bwd (tail = the quantiser's producer)")
     ap.add_argument("--no-graphs", action="store_true", help="eager step loop in the timed region instead of CUDA-graph replay")
+    ap.add_argument("--cudnn-benchmark", type=int, default=CUDNN_BENCHMARK, choices=[0, 1],
+                    help="VQ-W-Net legs: torch.backends.cudnn.benchmark for the stock convolutions around the quantiser")
     args = ap.parse_args()
+    globals()["CUDNN_BENCHMARK"] = args.cudnn_benchmark
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload in ("vqwnet", "vqwnet512"):
         return run_wnet_reference_arm(args) if args.impl == "reference" else run_wnet_b200_arm(args)

@@ -18,11 +18,15 @@ Nothing here touches the CUDA kernels; it runs on `gloo`/CPU for the host-logic 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, Optional
 
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
+
+
+_FUSED_ADAM = os.environ.get("VQ_TRAINER_FUSED_ADAM", "0") == "1"      # default optimiser only; see DESIGN section 5
 
 
 def _world(group=None) -> int:
@@ -171,7 +175,11 @@ class DataParallelVQTrainer:
             if hasattr(mod, "reduce_mode") and hasattr(mod, "embed_avg"):
                 mod.reduce_mode = "sum"
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(self.params, lr=lr)
+        if optimizer is None:
+            # one multi-tensor kernel per step instead of torch's per-operation `foreach` passes (same update rule)
+            fused = _FUSED_ADAM and all(p.is_cuda for p in self.params)
+            optimizer = torch.optim.Adam(self.params, lr=lr, fused=True) if fused else torch.optim.Adam(self.params, lr=lr)
+        self.optimizer = optimizer
         self.world_size = _world(group)
         self.buckets = GradientBuckets(self.params, group)
 
