@@ -762,7 +762,7 @@ def wnet_config(gpus, extra=None, name="vqwnet"):
     B, H, micro = wnet_shape(name, gpus)
     c = {"workload": f"{name}: VQ-W-Net training step (tools/wnet.py = vqwnet.py topology, filters 64..1024, K = {WNET['K']}; "
                      f"loss = mse(recon, x) + commit_loss, Adam lr 1e-4), batch {B} of 1x{H}x{H} "
-                     "synthetic slices per GPU, fp32 (cuDNN convolutions at torch's default: TF32 allowed)"
+                     "synthetic slices per GPU, fp32 (stock cuDNN convolutions, TF32 allowed as torch defaults; cudnn.benchmark per the cudnn_benchmark key; Adam fused unless VQ_TRAINER_FUSED_ADAM=0)"
                      + (f"; global batch {WNET512_GLOBAL} (run_vqwnet.py:112-121), {micro} micro-batch(es) of {B // micro} slices per "
                         "step with gradients and EMA statistics accumulated, exchanged once" if name == "vqwnet512" else ""),
          "slices_per_gpu": B, "resolution": H, "dict_size": WNET["K"], "emb_dim": WNET["D"], "micro_batches": micro,
@@ -789,7 +789,7 @@ def fuse_wnet_norms(model, mode):
     return 0
 
 
-CUDNN_BENCHMARK = int(os.environ.get("VQ_BENCH_CUDNN_BENCHMARK", "0"))
+CUDNN_BENCHMARK = int(os.environ.get("VQ_BENCH_CUDNN_BENCHMARK", "1"))
 
 
 def measure_wnet_b200(dev, rank, world, steps, warmup, inline_exchange=False, name="vqwnet", fused_norm="none"):

@@ -37,6 +37,7 @@ const char* get_error();
 constexpr int kMaxDevices = 64;
 int current_device();                 // cudaGetDevice(), clamped to [0, kMaxDevices)
 int device_sm_count();                // multiprocessors of the current device (cached per device)
+int tuning_knob(const char* name, int dflt);   // integer environment switch, read at every call (A/B timing of launch shapes)
 
 // measurement hooks (vq_launch_count / vq_profile_*)
 void count_launch(int n = 1);

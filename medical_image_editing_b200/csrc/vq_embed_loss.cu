@@ -33,29 +33,38 @@ static inline ElWork carve_el(void* base, int B, int K) {
 }
 size_t embed_loss_work_bytes(int B, int K) { return carve_el(nullptr, B, K).bytes; }
 
-// add (v, 1) to table entry `key` for every lane with key >= 0; lanes with equal keys are combined first so that a
+// add (v, n) to table entry `key` for every lane with key >= 0; lanes with equal keys are combined first so that a
 // piecewise-constant label map (the usual case: neighbouring pixels share a class) costs one atomic per warp and class
-__device__ __forceinline__ void warp_group_add(int key, float v, double* sums, int* counts) {
+__device__ __forceinline__ void warp_group_add(int key, float v, int n, double* sums, int* counts) {
   const unsigned full = 0xffffffffu;
   const unsigned grp = __match_any_sync(full, key);
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(grp) - 1;
   float tot = 0.f;
-  for (unsigned rest = grp; rest; rest &= rest - 1) tot += __shfl_sync(grp, v, __ffs(rest) - 1);   // fixed (lane) order
+  int cnt = 0;
+  for (unsigned rest = grp; rest; rest &= rest - 1) {                       // fixed (lane) order
+    tot += __shfl_sync(grp, v, __ffs(rest) - 1);
+    cnt += __shfl_sync(grp, n, __ffs(rest) - 1);
+  }
   if (lane == leader && key >= 0) {
     atomicAdd(sums + key, (double)tot);
-    atomicAdd(counts + key, __popc(grp));
+    if (counts) atomicAdd(counts + key, cnt);
   }
 }
 
 // thread = 4 consecutive pixels (HW % 4 == 0): float4 streaming loads of z along the pixels, code rows through L1
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ labels, const float* __restrict__ E,
                        int D, int HW, int K, long long nquads, double* __restrict__ sums, int* __restrict__ counts,
-                       int nrep, int table) {
+                       int nrep, int table, int dsplit) {
+  // blockIdx.y = slice of the channels (finer CTAs: the grid is only ~2 waves of whole-pixel CTAs otherwise); the pixel
+  // counts come from slice 0 alone
   sums += (size_t)(blockIdx.x % nrep) * table;
   counts += (size_t)(blockIdx.x % nrep) * table;
   const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int dper = D / dsplit;                   // dsplit > 1 only when D % (4 * dsplit) == 0
+  const int dbeg = blockIdx.y * dper, dend = dbeg + dper;
   int key[4] = {-1, -1, -1, -1};
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (quad < nquads) {
@@ -72,9 +81,9 @@ vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ 
       er[i] = E + (size_t)(ok ? lab[i] - 1 : 0) * D;
     }
     const long long base = b * (long long)D * HW + p;
-    int d = 0;
-    if ((D & 3) == 0 && ((uintptr_t)E & 15) == 0) {
-      for (; d < D; d += 4) {                       // four channels per step: float4 loads of the code rows too
+    int d = dbeg;
+    if ((D & 3) == 0 && (dper & 3) == 0 && ((uintptr_t)E & 15) == 0) {
+      for (; d < dend; d += 4) {                    // four channels per step: float4 loads of the code rows too
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(er[0] + d));
         const float4 a1 = __ldg(reinterpret_cast<const float4*>(er[1] + d));
         const float4 a2 = __ldg(reinterpret_cast<const float4*>(er[2] + d));
@@ -94,7 +103,7 @@ vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ 
         }
       }
     }
-    for (; d < D; ++d) {
+    for (; d < dend; ++d) {
       const float4 zv = __ldcs(reinterpret_cast<const float4*>(z + base + (long long)d * HW));
       const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
@@ -104,9 +113,24 @@ vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ 
       }
     }
   }
+  // a thread's four pixels usually share a class: fold equal keys inside the thread first (a quarter of the atomics on
+  // piecewise-constant maps), then across the warp
+  int cnt[4] = {1, 1, 1, 1};
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      if (key[i] >= 0 && key[i] == key[j]) {
+        acc[j] += acc[i];
+        cnt[j] += cnt[i];
+        key[i] = -1;
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (__any_sync(0xffffffffu, key[i] >= 0)) warp_group_add(key[i], acc[i], sums, counts);
+    if (__any_sync(0xffffffffu, key[i] >= 0))
+      warp_group_add(key[i], acc[i], cnt[i], sums, blockIdx.y == 0 ? counts : nullptr);
   }
 }
 
@@ -134,7 +158,7 @@ vq_el_accum_generic_kernel(const float* __restrict__ z, const int32_t* __restric
       }
     }
   }
-  if (__any_sync(0xffffffffu, key >= 0)) warp_group_add(key, acc, sums, counts);
+  if (__any_sync(0xffffffffu, key >= 0)) warp_group_add(key, acc, 1, sums, counts);
 }
 
 // one CTA: loss = mean over present (b, k) of sums / (count + eps); weights for the backward pass
@@ -259,6 +283,16 @@ vq_el_bwd_generic_kernel(const float* __restrict__ g_loss, const float* __restri
 
 static int el_sm_count() { return device_sm_count(); }
 
+#ifndef VQ_EL_ACC_MINB_DEFAULT
+#define VQ_EL_ACC_MINB_DEFAULT 0
+#endif
+#ifndef VQ_EL_ACC_DSPLIT_DEFAULT
+#define VQ_EL_ACC_DSPLIT_DEFAULT 1
+#endif
+#ifndef VQ_EL_BWD_DSPLIT_DEFAULT
+#define VQ_EL_BWD_DSPLIT_DEFAULT 4
+#endif
+
 int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* embed, int B, int D, int H, int W, int K,
                           float* loss, float* weights, void* work, cudaStream_t s) {
   const int HW = H * W;
@@ -269,7 +303,17 @@ int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* em
     const bool vec = (HW % 4 == 0) && ((((uintptr_t)z) | ((uintptr_t)labels)) & 15) == 0;
     if (vec) {
       const long long nquads = N / 4;
-      vq_el_accum_vec_kernel<<<(unsigned)((nquads + 255) / 256), 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K);
+      int dsplit = 1;
+      const int want = tuning_knob("VQ_EL_ACC_DSPLIT", VQ_EL_ACC_DSPLIT_DEFAULT);
+      while (dsplit < want && D % (dsplit * 8) == 0) dsplit *= 2;
+      dim3 grid((unsigned)((nquads + 255) / 256), (unsigned)dsplit);
+      const int minb = tuning_knob("VQ_EL_ACC_MINB", VQ_EL_ACC_MINB_DEFAULT);      // register cap -> resident CTAs per SM
+      if (minb >= 6)
+        vq_el_accum_vec_kernel<6><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
+      else if (minb >= 5)
+        vq_el_accum_vec_kernel<5><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
+      else
+        vq_el_accum_vec_kernel<0><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
     } else {
       vq_el_accum_generic_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(z, labels, embed, D, HW, K, N, w.sums, w.counts, w.nrep, B * K);
     }
@@ -293,6 +337,8 @@ int launch_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* la
     const long long bx = (nquads + 255) / 256;
     int dsplit = 1;
     while (bx * dsplit < 4LL * el_sm_count() && D % (dsplit * 2) == 0) dsplit *= 2;
+    const int want = tuning_knob("VQ_EL_BWD_DSPLIT", VQ_EL_BWD_DSPLIT_DEFAULT);
+    while (dsplit < want && D % (dsplit * 8) == 0 && D / (dsplit * 2) >= 16) dsplit *= 2;
     dim3 grid((unsigned)bx, (unsigned)dsplit);
     vq_el_bwd_vec_kernel<<<grid, 256, 0, s>>>(g_loss, z, labels, embed, weights, g_z, D, HW, K, nquads, dsplit);
   } else {

@@ -595,7 +595,8 @@ vq_ema_embed_kd_kernel(const float* __restrict__ cluster_size, float* __restrict
 // backward:  g_z = g_q + g_loss * 2 (z - E[id]) / numel
 // =============================================================================================
 // vector path: thread = 4 consecutive pixels x 4 channels per step
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 vq_bwd_vec_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss, const float* __restrict__ z,
                   const int32_t* __restrict__ ids_nat, const float* __restrict__ E, float* __restrict__ g_z,
                   int D, int HW, long long nquads, int dsplit, float two_over_numel) {
@@ -781,6 +782,11 @@ int device_sm_count() {
 
 static int sm_count() { return device_sm_count(); }
 
+int tuning_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 int launch_prep(const FwdArgs& a, bool tc_path, cudaStream_t s) {
   const int Kpad = pad_codes(a.K);
   const size_t work = (size_t)a.D * Kpad;
@@ -883,6 +889,16 @@ int launch_ema(float* cluster_size, float* embed_avg, long long avg_sd, long lon
   return VQ_OK;
 }
 
+#ifndef VQ_BWD_DSPLIT_DEFAULT
+#define VQ_BWD_DSPLIT_DEFAULT 4
+#endif
+#ifndef VQ_BWD_MINB_DEFAULT
+#define VQ_BWD_MINB_DEFAULT 4
+#endif
+#ifndef VQ_LOOKUP_MINB_DEFAULT
+#define VQ_LOOKUP_MINB_DEFAULT 4
+#endif
+
 int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int32_t* ids_nat, const float* snap,
                float* g_z, int B, int D, int H, int W, int K, cudaStream_t s) {
   (void)K;
@@ -898,8 +914,15 @@ int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int3
     // split the channel loop across blockIdx.y until the grid has a few waves
     int dsplit = 1;
     while (bx * dsplit < 4LL * sm_count() && (D / (dsplit * 2)) % 4 == 0 && D / (dsplit * 2) >= 4) dsplit *= 2;
+    // finer CTAs (>= 16 channels each): at config 2 the grid is only 2.3 waves of whole-pixel CTAs; measured 0.147 -> 0.129 ms
+    // (0.85 -> 0.96 of the HBM peak) with four channel slices and the 64-register build (tools/knob_ab.py, profiles/r02_knob_ab.jsonl)
+    const int want = tuning_knob("VQ_BWD_DSPLIT", VQ_BWD_DSPLIT_DEFAULT);
+    while (dsplit < want && (D / (dsplit * 2)) % 4 == 0 && D / (dsplit * 2) >= 16) dsplit *= 2;
     dim3 grid((unsigned)bx, (unsigned)dsplit);
-    vq_bwd_vec_kernel<<<grid, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, nquads, dsplit, two_over_numel);
+    if (tuning_knob("VQ_BWD_MINB", VQ_BWD_MINB_DEFAULT) >= 4)
+      vq_bwd_vec_kernel<4><<<grid, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, nquads, dsplit, two_over_numel);
+    else
+      vq_bwd_vec_kernel<0><<<grid, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, nquads, dsplit, two_over_numel);
   } else {
     const long long bx = (N + 255) / 256;
     vq_bwd_generic_kernel<<<(unsigned)bx, 256, 0, s>>>(g_q, g_loss, z, ids_nat, snap, g_z, D, HW, N, two_over_numel);
@@ -912,8 +935,8 @@ int launch_bwd(const float* g_q, const float* g_loss, const float* z, const int3
 // Same gather, 64 a x 16 c tiles (A % 4 == 0, out 16-byte aligned): every (channel, c) row of the tile is 256 contiguous
 // bytes of the output (the 32 x 32 tile wrote 128-byte pieces 2 KB apart: poor DRAM page locality for a pure write
 // stream), the ids are still read in full 128-byte rows.  thread = four consecutive a of one c.
-template <int TA, int TC>
-__global__ void __launch_bounds__(256)
+template <int TA, int TC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 vq_lookup_nchw_tw_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, int K, int D,
                           float* __restrict__ out, int B, int A, int C, int* __restrict__ status) {
   static_assert(TA * TC == 1024 && TA % 4 == 0, "256 threads x 4 pixels");
@@ -983,13 +1006,16 @@ int launch_lookup(const int64_t* ids, int64_t n, const float* embed, int K, int 
     if (t64 < 0) { const char* e = getenv("VQ_LOOKUP_T64"); t64 = e ? atoi(e) : 1; }
     if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 1) {
       dim3 g64((A + 63) / 64, (C + 15) / 16, B);
-      vq_lookup_nchw_tw_kernel<64, 16><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+      const int minb = tuning_knob("VQ_LOOKUP_MINB", VQ_LOOKUP_MINB_DEFAULT);   // register cap -> resident CTAs per SM
+      if (minb >= 5) vq_lookup_nchw_tw_kernel<64, 16, 5><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+      else if (minb >= 4) vq_lookup_nchw_tw_kernel<64, 16, 4><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+      else vq_lookup_nchw_tw_kernel<64, 16, 0><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
     } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 2) {
       dim3 g64((A + 127) / 128, (C + 7) / 8, B);
-      vq_lookup_nchw_tw_kernel<128, 8><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+      vq_lookup_nchw_tw_kernel<128, 8, 0><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
     } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0 && t64 == 3) {
       dim3 g64((A + 255) / 256, (C + 3) / 4, B);
-      vq_lookup_nchw_tw_kernel<256, 4><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
+      vq_lookup_nchw_tw_kernel<256, 4, 0><<<g64, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
     } else if ((A & 3) == 0 && (((uintptr_t)out) & 15) == 0)
       vq_lookup_nchw_t_kernel<true><<<grid, 256, 0, s>>>(ids, embed, K, D, out, B, A, C, status);
     else

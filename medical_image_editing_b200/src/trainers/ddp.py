@@ -26,7 +26,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 
-_FUSED_ADAM = os.environ.get("VQ_TRAINER_FUSED_ADAM", "0") == "1"      # default optimiser only; see DESIGN section 5
+_FUSED_ADAM = os.environ.get("VQ_TRAINER_FUSED_ADAM", "1") == "1"      # default optimiser only; see DESIGN section 5
 
 
 def _world(group=None) -> int:
