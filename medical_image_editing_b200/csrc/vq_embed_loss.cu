@@ -57,7 +57,7 @@ template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
 vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ labels, const float* __restrict__ E,
                        int D, int HW, int K, long long nquads, double* __restrict__ sums, int* __restrict__ counts,
-                       int nrep, int table, int dsplit) {
+                       int nrep, int table, int dsplit, int same_row) {
   // blockIdx.y = slice of the channels (finer CTAs: the grid is only ~2 waves of whole-pixel CTAs otherwise); the pixel
   // counts come from slice 0 alone
   sums += (size_t)(blockIdx.x % nrep) * table;
@@ -82,7 +82,27 @@ vq_el_accum_vec_kernel(const float* __restrict__ z, const int32_t* __restrict__ 
     }
     const long long base = b * (long long)D * HW + p;
     int d = dbeg;
-    if ((D & 3) == 0 && (dper & 3) == 0 && ((uintptr_t)E & 15) == 0) {
+    const bool vec_rows = (D & 3) == 0 && (dper & 3) == 0 && ((uintptr_t)E & 15) == 0;
+    if (vec_rows && same_row && lab[0] == lab[1] && lab[1] == lab[2] && lab[2] == lab[3]) {
+      // the four pixels share a class (the usual case on a segmentation map): ONE code-row load per step instead of
+      // four -- the scattered 16-byte row loads, not the z stream, are what fills the L1 wavefront budget here (a warp's
+      // row load touches up to 16 lines, its z load 4).  Same operations per pixel in the same order: bit-identical.
+      for (; d < dend; d += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(er[0] + d));
+        const float ev[4] = {a.x, a.y, a.z, a.w};
+        float4 zv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zv[c] = __ldcs(reinterpret_cast<const float4*>(z + base + (long long)(d + c) * HW));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float d0 = zv[c].x - ev[c], d1 = zv[c].y - ev[c], d2 = zv[c].z - ev[c], d3 = zv[c].w - ev[c];
+          acc[0] = __fmaf_rn(d0, d0, acc[0]);
+          acc[1] = __fmaf_rn(d1, d1, acc[1]);
+          acc[2] = __fmaf_rn(d2, d2, acc[2]);
+          acc[3] = __fmaf_rn(d3, d3, acc[3]);
+        }
+      }
+    } else if (vec_rows) {
       for (; d < dend; d += 4) {                    // four channels per step: float4 loads of the code rows too
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(er[0] + d));
         const float4 a1 = __ldg(reinterpret_cast<const float4*>(er[1] + d));
@@ -208,10 +228,11 @@ vq_el_finish_kernel(const double* __restrict__ sums, const int* __restrict__ cou
 }
 
 // backward: g_z = g_loss * 2 * w[b, k] * (z - c_k) for labelled pixels, 0 elsewhere
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 vq_el_bwd_vec_kernel(const float* __restrict__ g_loss, const float* __restrict__ z, const int32_t* __restrict__ labels,
                      const float* __restrict__ E, const float* __restrict__ weights, float* __restrict__ g_z,
-                     int D, int HW, int K, long long nquads, int dsplit) {
+                     int D, int HW, int K, long long nquads, int dsplit, int same_row) {
   const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (quad >= nquads) return;
   const int qpi = HW >> 2;
@@ -232,7 +253,25 @@ vq_el_bwd_vec_kernel(const float* __restrict__ g_loss, const float* __restrict__
   const int dbeg = blockIdx.y * dper, dend = dbeg + dper;
   const long long base = b * (long long)D * HW + p;
   int d = dbeg;
-  if ((dper & 3) == 0 && ((uintptr_t)E & 15) == 0 && (D & 3) == 0) {
+  const bool vec_rows = (dper & 3) == 0 && ((uintptr_t)E & 15) == 0 && (D & 3) == 0;
+  if (vec_rows && same_row && lab[0] == lab[1] && lab[1] == lab[2] && lab[2] == lab[3]) {
+    for (; d < dend; d += 4) {                      // one class for the four pixels: one code-row load per step (see the accumulation)
+      const float4 a = __ldg(reinterpret_cast<const float4*>(er[0] + d));
+      const float ev[4] = {a.x, a.y, a.z, a.w};
+      float4 zv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) zv[c] = __ldcs(reinterpret_cast<const float4*>(z + base + (long long)(d + c) * HW));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 r;
+        r.x = coef[0] * (zv[c].x - ev[c]);
+        r.y = coef[1] * (zv[c].y - ev[c]);
+        r.z = coef[2] * (zv[c].z - ev[c]);
+        r.w = coef[3] * (zv[c].w - ev[c]);
+        __stcs(reinterpret_cast<float4*>(g_z + base + (long long)(d + c) * HW), r);
+      }
+    }
+  } else if (vec_rows) {
     for (; d < dend; d += 4) {                      // four channels per step: float4 loads of the code rows (as vq_bwd_vec)
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(er[0] + d));
       const float4 a1 = __ldg(reinterpret_cast<const float4*>(er[1] + d));
@@ -283,8 +322,14 @@ vq_el_bwd_generic_kernel(const float* __restrict__ g_loss, const float* __restri
 
 static int el_sm_count() { return device_sm_count(); }
 
+#ifndef VQ_EL_SAMEROW_DEFAULT
+#define VQ_EL_SAMEROW_DEFAULT 1
+#endif
+#ifndef VQ_EL_BWD_MINB_DEFAULT
+#define VQ_EL_BWD_MINB_DEFAULT 4
+#endif
 #ifndef VQ_EL_ACC_MINB_DEFAULT
-#define VQ_EL_ACC_MINB_DEFAULT 0
+#define VQ_EL_ACC_MINB_DEFAULT 4
 #endif
 #ifndef VQ_EL_ACC_DSPLIT_DEFAULT
 #define VQ_EL_ACC_DSPLIT_DEFAULT 1
@@ -307,13 +352,16 @@ int launch_embed_loss_fwd(const float* z, const int32_t* labels, const float* em
       const int want = tuning_knob("VQ_EL_ACC_DSPLIT", VQ_EL_ACC_DSPLIT_DEFAULT);
       while (dsplit < want && D % (dsplit * 8) == 0) dsplit *= 2;
       dim3 grid((unsigned)((nquads + 255) / 256), (unsigned)dsplit);
+      const int same_row = tuning_knob("VQ_EL_SAMEROW", VQ_EL_SAMEROW_DEFAULT);
       const int minb = tuning_knob("VQ_EL_ACC_MINB", VQ_EL_ACC_MINB_DEFAULT);      // register cap -> resident CTAs per SM
       if (minb >= 6)
-        vq_el_accum_vec_kernel<6><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
+        vq_el_accum_vec_kernel<6><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit, same_row);
       else if (minb >= 5)
-        vq_el_accum_vec_kernel<5><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
+        vq_el_accum_vec_kernel<5><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit, same_row);
+      else if (minb >= 4)
+        vq_el_accum_vec_kernel<4><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit, same_row);
       else
-        vq_el_accum_vec_kernel<0><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit);
+        vq_el_accum_vec_kernel<0><<<grid, 256, 0, s>>>(z, labels, embed, D, HW, K, nquads, w.sums, w.counts, w.nrep, B * K, dsplit, same_row);
     } else {
       vq_el_accum_generic_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(z, labels, embed, D, HW, K, N, w.sums, w.counts, w.nrep, B * K);
     }
@@ -340,7 +388,11 @@ int launch_embed_loss_bwd(const float* g_loss, const float* z, const int32_t* la
     const int want = tuning_knob("VQ_EL_BWD_DSPLIT", VQ_EL_BWD_DSPLIT_DEFAULT);
     while (dsplit < want && D % (dsplit * 8) == 0 && D / (dsplit * 2) >= 16) dsplit *= 2;
     dim3 grid((unsigned)bx, (unsigned)dsplit);
-    vq_el_bwd_vec_kernel<<<grid, 256, 0, s>>>(g_loss, z, labels, embed, weights, g_z, D, HW, K, nquads, dsplit);
+    const int same_row = tuning_knob("VQ_EL_SAMEROW", VQ_EL_SAMEROW_DEFAULT);
+    if (tuning_knob("VQ_EL_BWD_MINB", VQ_EL_BWD_MINB_DEFAULT) >= 4)
+      vq_el_bwd_vec_kernel<4><<<grid, 256, 0, s>>>(g_loss, z, labels, embed, weights, g_z, D, HW, K, nquads, dsplit, same_row);
+    else
+      vq_el_bwd_vec_kernel<0><<<grid, 256, 0, s>>>(g_loss, z, labels, embed, weights, g_z, D, HW, K, nquads, dsplit, same_row);
   } else {
     vq_el_bwd_generic_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(g_loss, z, labels, embed, weights, g_z, D, HW, K, N);
   }
