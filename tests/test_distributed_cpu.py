@@ -215,3 +215,16 @@ def test_trainer_micro_batches_equal_one_shot_step():
         tr2.training_step(x, micro_batches=4)
     for p2, p in zip(model2.parameters(), model.parameters()):
         assert np.allclose(p2.detach().numpy(), p.detach().numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_trainer_default_optimizer_is_fused_only_on_cuda():
+    """The trainer's default Adam is the fused multi-tensor kernel only when every parameter lives on a GPU (DESIGN
+    section 5); on the CPU (these tests, the gloo ranks) it stays torch's stock implementation."""
+    import torch
+    from medical_image_editing_b200.src.trainers.ddp import DataParallelVQTrainer
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 2, 3, padding=1))
+    tr = DataParallelVQTrainer(net, lr=1e-3)
+    assert isinstance(tr.optimizer, torch.optim.Adam)
+    assert not tr.optimizer.defaults.get("fused")
+    own = torch.optim.SGD(net.parameters(), lr=0.1)
+    assert DataParallelVQTrainer(net, optimizer=own).optimizer is own
